@@ -1,0 +1,307 @@
+/*
+ * rstsr_cuda.h -- C ABI of the B200-native `DeviceCuda` backend for rstsr.
+ *
+ * This is the drop-in boundary: one entry point per *trait method family* of the
+ * reference's device-trait surface (citations are paths inside RESTGroup/rstsr
+ * v0.7.10).  Plain pointers and sizes only; dtype and op are enums.  All
+ * `void *` tensor arguments are DEVICE pointers to the start of the raw storage
+ * (the reference's `Raw`), layouts address them in ELEMENTS (shape, stride, offset;
+ * strides may be zero or negative), exactly like `Layout<D>`
+ * (rstsr-common/src/layout/layoutbase.rs:15-23).
+ *
+ * Every function returns an `rc_status` (0 = ok).  The message of the last failure on
+ * the calling thread is available from `rc_last_error()`; nothing aborts or throws
+ * across the boundary.  The reference's `Result<T>` / `RSTSRError` kinds
+ * (rstsr-common/src/error.rs:12-49) map onto `rc_status`.
+ *
+ * Ops are stream-ordered on the device handle's stream.  Entry points that return
+ * host-visible data (`rc_reduce_all`, `rc_memcpy_d2h`, `rc_get_index`) synchronise
+ * before returning, so -- like the reference -- every result is complete when the
+ * caller can observe it.
+ *
+ * There is NO CPU fallback: if the CUDA runtime or a device is unavailable every
+ * compute entry point fails with RC_ERR_DEVICE.
+ */
+#ifndef RSTSR_CUDA_H
+#define RSTSR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_MAX_NDIM 16
+
+/* ---- status codes: mirror RSTSRError (rstsr-common/src/error.rs:12-49) ---- */
+typedef enum rc_status {
+    RC_OK = 0,
+    RC_ERR_VALUE_OUT_OF_RANGE = 1,
+    RC_ERR_INVALID_VALUE = 2,
+    RC_ERR_INVALID_LAYOUT = 3,
+    RC_ERR_RUNTIME = 4,
+    RC_ERR_DEVICE_MISMATCH = 5,
+    RC_ERR_UNIMPLEMENTED = 6,
+    RC_ERR_MEMORY = 7,
+    RC_ERR_DEVICE = 8, /* CUDA / NCCL failure -> RSTSRError::DeviceError(String) */
+    RC_ERR_INDEX = 9
+} rc_status;
+
+/* ---- element types; codes are stable ---- */
+typedef enum rc_dtype {
+    RC_BOOL = 0, /* 1 byte, 0/1 (Rust `bool`) */
+    RC_I8 = 1,
+    RC_I16 = 2,
+    RC_I32 = 3,
+    RC_I64 = 4, /* also isize */
+    RC_U8 = 5,
+    RC_U16 = 6,
+    RC_U32 = 7,
+    RC_U64 = 8, /* also usize */
+    RC_F32 = 9,
+    RC_F64 = 10
+} rc_dtype;
+
+/* FlagOrder (rstsr-common/src/flags.rs:60-87) */
+typedef enum rc_order { RC_ROW_MAJOR = 0, RC_COL_MAJOR = 1 } rc_order;
+
+/* TensorIterOrder subset accepted for copies (rstsr-common/src/flags.rs:92-136) */
+typedef enum rc_iter_order { RC_ITER_C = 0, RC_ITER_F = 1, RC_ITER_A = 2, RC_ITER_K = 3 } rc_iter_order;
+
+/* Layout<IxD>: rstsr-common/src/layout/layoutbase.rs:15-23 */
+typedef struct rc_layout {
+    int32_t ndim;
+    int64_t shape[RC_MAX_NDIM];
+    int64_t stride[RC_MAX_NDIM]; /* in elements; 0 = broadcast, < 0 = flipped */
+    int64_t offset;              /* in elements, >= 0 */
+} rc_layout;
+
+/* "ternary" ops c = a o b: Op{Add..Shr}API (rstsr-core/src/operators/ops/op_ternary_arithmetic.rs:16-48)
+ * and the binary-function traits (rstsr-core/src/operators/ops/op_ternary_common.rs:3-102). */
+typedef enum rc_binop {
+    RC_ADD = 0,
+    RC_SUB = 1,
+    RC_MUL = 2,
+    RC_DIV = 3,
+    RC_REM = 4,
+    RC_BITOR = 5,
+    RC_BITAND = 6,
+    RC_BITXOR = 7,
+    RC_SHL = 8,
+    RC_SHR = 9,
+    /* same-type function ops */
+    RC_MAXIMUM = 10,
+    RC_MINIMUM = 11,
+    RC_FLOOR_DIVIDE = 12,
+    RC_POW = 13,
+    RC_ATAN2 = 14,
+    RC_COPYSIGN = 15,
+    RC_HYPOT = 16,
+    RC_LOGADDEXP = 17,
+    RC_NEXTAFTER = 18,
+    /* comparison ops: output dtype is RC_BOOL */
+    RC_EQ = 32,
+    RC_NE = 33,
+    RC_LT = 34,
+    RC_LE = 35,
+    RC_GT = 36,
+    RC_GE = 37
+} rc_binop;
+
+/* unary ops a = f(b): OpNeg/NotAPI (ops/op_binary_arithmetic.rs:90-109) and the unary
+ * math traits (ops/op_binary_common.rs:3-57). */
+typedef enum rc_unop {
+    RC_NEG = 0,
+    RC_NOT = 1,
+    RC_ABS = 2,
+    RC_SQUARE = 3,
+    RC_SIGN = 4,
+    RC_SQRT = 5,
+    RC_EXP = 6,
+    RC_EXPM1 = 7,
+    RC_LOG = 8,
+    RC_LOG2 = 9,
+    RC_LOG10 = 10,
+    RC_SIN = 11,
+    RC_COS = 12,
+    RC_TAN = 13,
+    RC_ASIN = 14,
+    RC_ACOS = 15,
+    RC_ATAN = 16,
+    RC_SINH = 17,
+    RC_COSH = 18,
+    RC_TANH = 19,
+    RC_ASINH = 20,
+    RC_ACOSH = 21,
+    RC_ATANH = 22,
+    RC_FLOOR = 23,
+    RC_CEIL = 24,
+    RC_ROUND = 25,
+    RC_TRUNC = 26,
+    RC_RECIPROCAL = 27, /* also OpInvAPI */
+    RC_CONJ = 28,       /* identity on real types */
+    RC_REAL = 29,       /* identity on real types */
+    RC_IMAG = 30,       /* zero on real types */
+    /* boolean-output predicates: output dtype is RC_BOOL */
+    RC_ISNAN = 48,
+    RC_ISINF = 49,
+    RC_ISFINITE = 50,
+    RC_SIGNBIT = 51
+} rc_unop;
+
+/* reductions: Op{Sum,Min,Max,Prod,Mean}API (rstsr-core/src/operators/reduction.rs:3-33) */
+typedef enum rc_redop { RC_SUM = 0, RC_PROD = 1, RC_MAX = 2, RC_MIN = 3, RC_MEAN = 4 } rc_redop;
+
+typedef struct rc_device rc_device; /* opaque: {ordinal, default_order, stream, workspaces} */
+
+/* ------------------------------------------------------------------------------------------
+ * Library / error plumbing
+ * ---------------------------------------------------------------------------------------- */
+const char *rc_last_error(void);  /* thread-local message of the last non-OK status */
+const char *rc_version(void);     /* "rstsr-cuda <semver> sm_100a" */
+int rc_device_count(int *count);  /* number of visible CUDA devices */
+
+/* ------------------------------------------------------------------------------------------
+ * DeviceBaseAPI (rstsr-core/src/storage/device.rs:3-7; DeviceFaer impl device_faer/device.rs:46-60)
+ * ---------------------------------------------------------------------------------------- */
+int rc_device_create(int ordinal, rc_order default_order, rc_device **out);
+/* same, but ops are enqueued on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int rc_device_create_on_stream(int ordinal, rc_order default_order, void *cuda_stream, rc_device **out);
+int rc_device_destroy(rc_device *dev);
+int rc_device_default_order(const rc_device *dev, rc_order *out);
+int rc_device_set_default_order(rc_device *dev, rc_order order);
+int rc_device_same_device(const rc_device *a, const rc_device *b, int *same); /* ordinal & order equal */
+int rc_device_ordinal(const rc_device *dev, int *ordinal);
+int rc_device_stream(const rc_device *dev, void **cuda_stream);
+int rc_device_synchronize(rc_device *dev);
+/* number of kernels this handle has launched (bench.py's `gpu_launches`) */
+int rc_device_launch_count(const rc_device *dev, uint64_t *count);
+
+/* ------------------------------------------------------------------------------------------
+ * DeviceRawAPI / DeviceStorageAPI / DeviceCreationAnyAPI
+ * (storage/device.rs:9-54, storage/creation.rs:3-39, auto_impl/creation.rs:5-72)
+ *   uninit_impl/empty_impl -> rc_malloc          outof_cpu_vec/from_cpu_vec -> rc_malloc + rc_memcpy_h2d
+ *   to_cpu_vec/into_cpu_vec -> rc_memcpy_d2h     get_index/set_index -> rc_get_index/rc_set_index
+ *   zeros_impl -> rc_malloc + rc_memset          full_impl/ones_impl -> rc_malloc + rc_fill
+ *   Raw::clone -> rc_malloc + rc_memcpy_d2d      Raw::drop -> rc_free
+ * ---------------------------------------------------------------------------------------- */
+int rc_malloc(rc_device *dev, size_t nbytes, void **out);
+int rc_free(rc_device *dev, void *ptr);
+int rc_memcpy_h2d(rc_device *dev, void *dst_dev, const void *src_host, size_t nbytes);
+int rc_memcpy_d2h(rc_device *dev, void *dst_host, const void *src_dev, size_t nbytes); /* synchronises */
+int rc_memcpy_d2d(rc_device *dev, void *dst_dev, const void *src_dev, size_t nbytes);
+int rc_memset(rc_device *dev, void *dst_dev, int byte, size_t nbytes);
+int rc_get_index(rc_device *dev, rc_dtype dtype, const void *a, int64_t index, void *host_out);
+int rc_set_index(rc_device *dev, rc_dtype dtype, void *a, int64_t index, const void *host_value);
+/* pinned host staging buffers for outof_cpu_vec / to_cpu_vec */
+int rc_host_alloc(size_t nbytes, void **out);
+int rc_host_free(void *ptr);
+size_t rc_dtype_size(rc_dtype dtype);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side layout algebra: the parts of L0/L4 that decide what the device is asked to do and
+ * which layout the result has.  Reference-identical by contract.
+ * ---------------------------------------------------------------------------------------- */
+/* Layout::new validity: bounds_index + check_strides(skip_zero=true) (layoutbase.rs:237-320,396-404) */
+int rc_layout_check(const rc_layout *l);
+int rc_layout_bounds_index(const rc_layout *l, int64_t *min_out, int64_t *max_out);
+int rc_layout_c_contig(const rc_layout *l, int *out);
+int rc_layout_f_contig(const rc_layout *l, int *out);
+/* shape.c() / shape.f()  (layoutbase.rs:574-601) */
+int rc_layout_new_contig(const int64_t *shape, int ndim, rc_order order, int64_t offset, rc_layout *out);
+/* broadcast_layout (rstsr-common/src/layout/broadcast.rs:166-182) */
+int rc_layout_broadcast(const rc_layout *la, const rc_layout *lb, rc_order order, rc_layout *la_out,
+                        rc_layout *lb_out);
+/* get_layout_for_binary_op (rearrangement.rs:394-459): output layout of `a o b` (K iteration order) */
+int rc_layout_for_binary_op(const rc_layout *la, const rc_layout *lb, rc_order order, rc_layout *lc_out);
+/* layout_for_array_copy (rearrangement.rs:125-152): output layout of unary ops, scalar ops, to_owned */
+int rc_layout_for_array_copy(const rc_layout *la, rc_iter_order iter_order, rc_order default_order,
+                             rc_layout *lc_out);
+/* output layout of `*_axes` reductions: dim_split_axes (indexer.rs:453-478) + layout_for_array_copy(K)
+ * (cpu_rayon/reduction.rs:147-153). `axes` may be negative; duplicates are an error (axis_index.rs:379-414). */
+int rc_layout_for_reduce(const rc_layout *la, const int64_t *axes, int naxes, rc_layout *lo_out);
+/* layout_reshapeable (rstsr-common/src/layout/reshape.rs:216-226): *viewable = 1 and *out set when the
+ * reshape is a pure view; *viewable = 0 when a copy (rc_assign_arbitary) is needed. */
+int rc_layout_reshapeable(const rc_layout *la, const int64_t *shape, int ndim, rc_order order, int *viewable,
+                          rc_layout *out);
+/* Layout::eq (layoutbase.rs:547-572) -- used by to_layout to decide view-vs-copy (to_layout.rs:20) */
+int rc_layout_equal(const rc_layout *a, const rc_layout *b, int *equal);
+
+/* ------------------------------------------------------------------------------------------
+ * OpAssignAPI / OpAssignArbitaryAPI (rstsr-core/src/operators/assignment.rs:5-53;
+ * auto_impl/assignment.rs:3-49; loops cpu_rayon/assignment.rs:14-225)
+ * ---------------------------------------------------------------------------------------- */
+/* c[idx] = cast(a[idx]); lc and la have the same shape (already broadcast) */
+int rc_assign(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta, const void *a,
+              const rc_layout *la);
+/* k-th element of lc <- k-th element of la, k counted in the device's default order (C for row-major,
+ * F for col-major); shapes may differ, sizes must match.  (Reference spelling "arbitary" kept.) */
+int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta, const void *a,
+                       const rc_layout *la);
+/* c[idx] = cast(fill); *fill is a host scalar of dtype tf */
+int rc_fill(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype tf, const void *fill);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise (auto_impl/op_ternary_arithmetic.rs, op_ternary_common.rs, op_binary_arithmetic.rs,
+ * op_binary_common.rs; loops cpu_rayon/op_with_func.rs:13-390).
+ * `dtype` is the operand type TA = TB; the output type is `dtype`, except RC_BOOL for comparisons /
+ * predicates.  All layouts have the same shape (already broadcast by the caller).
+ * ---------------------------------------------------------------------------------------- */
+int rc_op_mutc_refa_refb(rc_device *dev, rc_binop op, rc_dtype dtype, void *c, const rc_layout *lc, const void *a,
+                         const rc_layout *la, const void *b, const rc_layout *lb);
+int rc_op_mutc_refa_numb(rc_device *dev, rc_binop op, rc_dtype dtype, void *c, const rc_layout *lc, const void *a,
+                         const rc_layout *la, const void *b_host_scalar);
+int rc_op_mutc_numa_refb(rc_device *dev, rc_binop op, rc_dtype dtype, void *c, const rc_layout *lc,
+                         const void *a_host_scalar, const void *b, const rc_layout *lb);
+/* in-place: a = a o b  (Op*AssignAPI, OpLConsume*API);  reverse != 0: a = b o a  (OpRConsume*API) */
+int rc_op_muta_refb(rc_device *dev, rc_binop op, rc_dtype dtype, void *a, const rc_layout *la, const void *b,
+                    const rc_layout *lb, int reverse);
+int rc_op_muta_numb(rc_device *dev, rc_binop op, rc_dtype dtype, void *a, const rc_layout *la,
+                    const void *b_host_scalar, int reverse);
+/* unary with output a = f(b) (dtype = type of b; output dtype per op) and in-place a = f(a) */
+int rc_unary_muta_refb(rc_device *dev, rc_unop op, rc_dtype dtype, void *a, const rc_layout *la, const void *b,
+                       const rc_layout *lb);
+int rc_unary_muta(rc_device *dev, rc_unop op, rc_dtype dtype, void *a, const rc_layout *la);
+/* output dtype of an elementwise op for operand dtype `dtype` (bool for comparisons/predicates) */
+int rc_binop_out_dtype(rc_binop op, rc_dtype dtype, rc_dtype *out);
+int rc_unop_out_dtype(rc_unop op, rc_dtype dtype, rc_dtype *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Reductions: Op{Sum,Prod,Max,Min,Mean}API (rstsr-core/src/operators/reduction.rs:3-33;
+ * auto_impl/reduction.rs:7-205; loops cpu_rayon/reduction.rs:20-328)
+ * ---------------------------------------------------------------------------------------- */
+/* `*_all` -> host scalar of type `dtype`.  max/min of a zero-size layout is RC_ERR_INVALID_VALUE. */
+int rc_reduce_all(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la, void *host_out);
+/* same, but the scalar stays on the device (dev_out: 1 element) and nothing synchronises: the
+ * per-GPU partial of a sharded reduction, to be combined by rc_comm_all_reduce. */
+int rc_reduce_all_device(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la,
+                         void *dev_out);
+/* `*_axes`: the CALLEE allocates the output (free with rc_free) and chooses its layout
+ * (operators/reduction.rs:26-32): *out_dev has lo_out->size() elements, lo_out == rc_layout_for_reduce(). */
+int rc_reduce_axes(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la,
+                   const int64_t *axes, int naxes, void **out_dev, rc_layout *lo_out);
+/* same into caller-provided storage with an explicit output layout (shape = kept axes of la) */
+int rc_reduce_axes_into(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la,
+                        const int64_t *axes, int naxes, void *out_dev, const rc_layout *lo);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: one process (or handle) per GPU; shards are independent except for reductions whose
+ * sharded axis is reduced.  The collective is NCCL all-reduce over NVLink.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rc_comm rc_comm;
+#define RC_COMM_ID_BYTES 128
+int rc_comm_get_unique_id(uint8_t id[RC_COMM_ID_BYTES]);
+int rc_comm_init_rank(rc_device *dev, int nranks, int rank, const uint8_t id[RC_COMM_ID_BYTES], rc_comm **out);
+int rc_comm_destroy(rc_comm *comm);
+/* in-place all-reduce of `count` elements with the reduction's combiner (sum/prod/max/min; mean = sum,
+ * the caller divides by the global count via rc_op_muta_numb) on the device's stream */
+int rc_comm_all_reduce(rc_comm *comm, rc_redop op, rc_dtype dtype, void *buf_dev, size_t count);
+/* sharded `*_all`: local partial + all-reduce + host scalar; n_global is the global element count (mean) */
+int rc_reduce_all_sharded(rc_device *dev, rc_comm *comm, rc_redop op, rc_dtype dtype, const void *a,
+                          const rc_layout *la, int64_t n_global, void *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSTSR_CUDA_H */

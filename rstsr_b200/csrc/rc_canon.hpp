@@ -1,0 +1,48 @@
+// rc_canon.hpp -- host canonicaliser: turns reference layouts into the compact descriptors the kernels
+// take by value.  This supersedes translate_to_col_major / translate_to_col_major_with_contig
+// (rstsr-common/src/layout/rearrangement.rs:232-322): it also drops extent-1 axes, flips axes the
+// output walks backwards, and merges every pair of axes that is jointly contiguous in all operands.
+#pragma once
+#include "rc_common.hpp"
+
+namespace rc {
+
+constexpr int KMAXD = 8;   // dims a kernel decomposes an index into (after merging)
+constexpr int KMAXOPS = 3; // operands of one elementwise launch (output first)
+
+// Same-shape operands, canonical axis order: dim 0 is the output's fastest axis.
+struct CanonEw {
+    int nops = 0;
+    int ndim = 0;                        // >= 1 unless empty
+    bool empty = false;                  // zero elements: nothing to launch
+    std::vector<int64_t> shape;          // [ndim]
+    std::vector<int64_t> stride[KMAXOPS];// [ndim] per operand, elements
+    int64_t base[KMAXOPS] = {0, 0, 0};   // element offset of index 0 per operand
+    int64_t total() const {
+        int64_t s = 1;
+        for (auto d : shape) s *= d;
+        return s;
+    }
+};
+
+// layouts[0] is the output.  `collapse_out_broadcast`: iteration order G (in-place unary / fill): axes
+// where the output has stride 0 are visited once.  A broadcast output is otherwise rejected.
+CanonEw canon_elementwise(const std::vector<const Layout *> &layouts, bool collapse_out_broadcast);
+
+// Rewrites (lc, la) of equal SIZE but different shape into two layouts of one common refined shape such
+// that same-index pairing equals flattened-order pairing in `order` (assign_arbitary semantics,
+// cpu_serial/assignment.rs:39-67).  Returns false if the two shapes have no common refinement.
+bool refine_to_common_shape(const Layout &lc, const Layout &la, rc_order order, Layout *oc, Layout *oa);
+
+// Reduction descriptor: kept axes (input stride, output stride) and reduced axes (input stride).
+struct CanonRed {
+    bool empty_out = false;              // no output elements
+    std::vector<int64_t> kshape, kstride_in, kstride_out;  // kept dims, dim 0 = fastest on the OUTPUT
+    std::vector<int64_t> rshape, rstride;                  // reduced dims, dim 0 = smallest |stride|
+    int64_t base_in = 0, base_out = 0;
+    int64_t n_out() const { int64_t s = 1; for (auto d : kshape) s *= d; return s; }
+    int64_t n_red() const { int64_t s = 1; for (auto d : rshape) s *= d; return s; }
+};
+CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layout &lo);
+
+}  // namespace rc

@@ -1,0 +1,47 @@
+// rc_device.hpp -- the device handle behind `rc_device *` and CUDA error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "rc_common.hpp"
+
+struct rc_device {
+    int ordinal = 0;
+    rc_order order = RC_ROW_MAJOR;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::atomic<uint64_t> launches{0};
+    // reduction workspace (partials of two-pass grid reductions), grown lazily
+    std::mutex ws_mu;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+namespace rc {
+
+#define RC_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            ::rc::raise(RC_ERR_DEVICE, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+// cudaSetDevice for the duration of one entry point
+struct DeviceGuard {
+    explicit DeviceGuard(const rc_device *d) {
+        RC_CHECK(d != nullptr, RC_ERR_INVALID_VALUE, "null device handle");
+        RC_CUDA(cudaSetDevice(d->ordinal));
+    }
+};
+
+inline void after_launch(rc_device *d, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) raise(RC_ERR_DEVICE, std::string(what) + " launch failed: " + cudaGetErrorString(e));
+    d->launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+void *workspace(rc_device *d, size_t nbytes);  // stream-ordered scratch, valid until the next call
+
+}  // namespace rc

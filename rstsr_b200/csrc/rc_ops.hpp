@@ -1,0 +1,29 @@
+// rc_ops.hpp -- typed dispatch entry points implemented by the .cu translation units.
+#pragma once
+#include "rc_canon.hpp"
+#include "rc_device.hpp"
+
+namespace rc {
+
+struct EwArgs;
+
+// c = a o b (arithmetic: rc_ew_arith.cu, bit ops: rc_ew_bit.cu, functions: rc_ew_func.cu, comparisons: rc_ew_cmp.cu)
+void run_binary_arith(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+void run_binary_bit(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+void run_binary_func(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+void run_binary_cmp(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+// a = f(b)
+void run_unary(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+// c = cast(a) (rc_copy.cu); same dtype moves raw bits
+void run_cast(rc_device *dev, rc_dtype tc, rc_dtype ta, const CanonEw &c, const EwArgs &args);
+// c = value (already of dtype tc, host memory)
+void run_fill(rc_device *dev, rc_dtype tc, const CanonEw &c, void *c_ptr, const void *value_tc);
+// generic flattened-order copy when two shapes have no common refinement (rc_copy.cu)
+void run_assign_arbitrary_generic(rc_device *dev, rc_dtype tc, void *c, const Layout &lc, rc_dtype ta, const void *a,
+                                  const Layout &la, rc_order order);
+
+// reductions (rc_reduce.cu): out has n_out elements laid out by `cr`
+void run_reduce(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out,
+                int64_t mean_count);
+
+}  // namespace rc
