@@ -43,7 +43,7 @@ struct ArbDesc {
 };
 
 template <class F>
-__global__ void __launch_bounds__(256) arb_kernel(const ArbDesc d, typename F::TO *c, const typename F::TA *a) {
+__global__ void __launch_bounds__(256) arb_kernel(const __grid_constant__ ArbDesc d, typename F::TO *c, const typename F::TA *a) {
     uint32_t idx = blockIdx.x * 256u + threadIdx.x;
     if (idx >= d.total) return;
     int64_t oc = 0, oa = 0;

@@ -1,4 +1,4 @@
-// rc_reduce.cu -- kernel families K3/K4: sum / prod / max / min / mean over all or selected axes.
+// rc_reduce.cuh -- kernel families K3/K4: sum / prod / max / min / mean over all or selected axes.
 //
 // Replaces rstsr-native-impl/src/cpu_rayon/reduction.rs:20-328 (reduce_all_cpu_rayon, reduce_axes_cpu_rayon)
 // with the (init, f, f_sum, f_out) monoids of rstsr-core/src/feature_rayon/auto_impl/reduction.rs:7-205:
@@ -7,13 +7,17 @@
 // the accumulator has the element type (f32 sums in f32); integer sums wrap.
 //
 //   reduce_rows_kernel  a group of G threads (1..256) owns one output and strides over the reduced index
-//                       space; when the smallest-stride reduced dim is contiguous it is read as 16-byte packs.
-//                       Warp-shuffle tree inside a warp, shared-memory tree across warps.
+//                       space; when the smallest-stride reduced dim is contiguous it is read as 32-byte packs
+//                       (256-bit LDG), 8 packs in flight per thread.  Warp-shuffle tree inside a warp,
+//                       shared-memory tree across warps.
 //   reduce_cols_kernel  the kept fastest axis is contiguous in input and output: lanes own columns
-//                       (16-byte packs), warps walk the reduced rows, coalesced 512 B per warp and row.
+//                       (32-byte packs), warps walk the reduced rows: coalesced 1 KiB per warp and row.
 // Both take a split factor S along the reduced space (gridDim.y); S > 1 writes partials[S][n_out] into the
 // device handle's workspace and a second launch of the same kernel folds them in a FIXED order: the result
 // is run-to-run deterministic (no float atomics), which the reference's rayon fold is not.
+//
+// Measured on B200 (scripts/membench.cu): a read-only stream needs >= 128 KB in flight per SM to reach
+// 6.7-7.0 TB/s; 256-bit loads x 8 per thread do, 128-bit x 4 stall at 6.1 TB/s.
 #pragma once
 #include <limits>
 
@@ -25,7 +29,7 @@ namespace rc {
 namespace {
 
 constexpr int RED_BLOCK = 256;
-constexpr int RED_UNROLL = 4;
+constexpr int RED_UNROLL = 8;
 
 struct RedDesc {
     int nk, nr;
@@ -39,7 +43,7 @@ struct RedDesc {
     int64_t n_out_total;        // elements of the output (partial row pitch)
     int64_t packs0;             // cols kernel: packs along kept dim 0
     int group;                  // rows kernel: threads per output
-    int tcol;                   // cols kernel: blockDim.x
+    int tcol;                   // cols kernel: threads along the kept axis
     int do_div;                 // mean: divide by div on the final write
     int to_partial;             // write un-finalised accumulators to the partial buffer
 };
@@ -54,10 +58,8 @@ template <class T> struct OpSum {
 template <class T> struct OpProd {
     static __device__ __forceinline__ T init() { return (T)1; }
     static __device__ __forceinline__ T f(T a, T b) {
-        if constexpr (std::is_integral<T>::value) {
-            if constexpr (sizeof(T) < 4) return (T)((unsigned)a * (unsigned)b);
-            else return (T)((typename std::make_unsigned<T>::type)a * (typename std::make_unsigned<T>::type)b);
-        } else return a * b;
+        if constexpr (std::is_integral<T>::value) return (T)((typename std::make_unsigned<T>::type)a * (typename std::make_unsigned<T>::type)b);
+        else return a * b;
     }
 };
 template <class T> struct OpMax {
@@ -78,53 +80,56 @@ template <class T> struct OpMin {
 };
 
 template <class T>
-__device__ __forceinline__ T finalize(T acc, const RedDesc &d, T div) {
+__device__ __forceinline__ T finalize(T acc, int do_div, T div) {
     if constexpr (std::is_floating_point<T>::value) {
-        if (d.do_div) return acc / div;
+        if (do_div) return acc / div;
     }
     return acc;
 }
 
-// offset of linear index `i` over dims [first, n) with the given strides
-__device__ __forceinline__ int64_t decompose(int64_t i, int first, int n, const int64_t *shape, const FastDiv *dv,
-                                             const int64_t *stride, int big) {
+// offset of linear index `i` over dims [first, n) with the given strides (cold path: kept never inlined in
+// the streaming loop unless the reduced space really is multi-dimensional)
+__device__ __noinline__ int64_t decompose_big(int64_t i, int first, int n, const int64_t *shape, const int64_t *stride) {
     int64_t off = 0;
-    if (!big) {
-        uint32_t t = (uint32_t)i;
-        for (int k = first; k < n; ++k) {
-            uint32_t q, r;
-            if (k + 1 < n) dv[k].divmod(t, q, r); else { q = 0; r = t; }
-            off += (int64_t)r * stride[k];
-            t = q;
-        }
-    } else {
-        for (int k = first; k < n; ++k) {
-            int64_t q, r;
-            if (k + 1 < n) { q = i / shape[k]; r = i - q * shape[k]; } else { q = 0; r = i; }
-            off += r * stride[k];
-            i = q;
-        }
+    for (int k = first; k < n; ++k) {
+        int64_t q, r;
+        if (k + 1 < n) { q = i / shape[k]; r = i - q * shape[k]; } else { q = 0; r = i; }
+        off += r * stride[k];
+        i = q;
     }
     return off;
 }
 
-template <class T, int W>
+__device__ __forceinline__ int64_t decompose(int64_t i, int first, int n, const int64_t *shape, const FastDiv *dv,
+                                             const int64_t *stride, int big) {
+    if (big) return decompose_big(i, first, n, shape, stride);
+    int64_t off = 0;
+    uint32_t t = (uint32_t)i;
+#pragma unroll 1
+    for (int k = first; k < n; ++k) {
+        uint32_t q, r;
+        if (k + 1 < n) dv[k].divmod(t, q, r); else { q = 0; r = t; }
+        off += (int64_t)r * stride[k];
+        t = q;
+    }
+    return off;
+}
+
+template <class T>
 __device__ __forceinline__ T shfl_xor_t(T v, int m) {
     if constexpr (sizeof(T) == 8) {
-        long long x = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long *>(&v), m, W);
-        return *reinterpret_cast<T *>(&x);
-    } else if constexpr (sizeof(T) == 4) {
-        int x = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<int *>(&v), m, W);
+        long long x = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long *>(&v), m);
         return *reinterpret_cast<T *>(&x);
     } else {
-        int x = __shfl_xor_sync(0xffffffffu, (int)v, m, W);
-        return (T)x;
+        int x = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<int *>(&v), m);
+        return *reinterpret_cast<T *>(&x);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <class Op, class T, int VEC>
-__global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const RedDesc d, const T *__restrict__ in,
+// MULTI: the reduced index space has more than one (non-mergeable) dim -> per-item decomposition.
+template <class Op, class T, int VEC, bool MULTI>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_constant__ RedDesc d, const T *__restrict__ in,
                                                                 T *__restrict__ out, T *__restrict__ partial,
                                                                 T div) {
     __shared__ T warp_acc[RED_BLOCK / 32];
@@ -133,9 +138,10 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const RedDesc d,
     const int g = tid / G, t = tid - g * G;
     const int64_t o = (int64_t)blockIdx.x * (RED_BLOCK / G) + g;
     const bool valid = o < d.n_out;
-    int64_t off_in = 0, off_out = 0;
+    int64_t off_out = 0;
+    const T *src = in;
     if (valid) {
-        off_in = decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
+        src += decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
         off_out = decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
     }
     const int64_t begin = (int64_t)blockIdx.y * d.chunk;
@@ -143,45 +149,46 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const RedDesc d,
     if (end > d.n_items) end = d.n_items;
     if (!valid) end = begin;
 
-    T acc[RED_UNROLL][VEC];
+    T acc[VEC];
 #pragma unroll
-    for (int u = 0; u < RED_UNROLL; ++u)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[u][j] = Op::init();
+    for (int j = 0; j < VEC; ++j) acc[j] = Op::init();
 
-    const int64_t step = (int64_t)G * RED_UNROLL;
     const int64_t rs0 = d.rs[0];  // per item (already multiplied by VEC for packs)
-    for (int64_t i = begin + t; i < end; i += step) {
+    int64_t i = begin + t;
+    // full groups: RED_UNROLL independent loads in flight, no per-load predicate
+    for (; i + (int64_t)(RED_UNROLL - 1) * G < end; i += (int64_t)G * RED_UNROLL) {
         Pack<T, VEC> p[RED_UNROLL];
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u) {
-            int64_t ii = i + (int64_t)u * G;
-            if (ii < end) {
-                int64_t off = (d.nr <= 1) ? ii * rs0 : decompose(ii, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
-                p[u] = ld_stream<T, VEC>(in + off_in + off);
-            } else {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) p[u].v[j] = Op::init();
-            }
+            const int64_t ii = i + (int64_t)u * G;
+            int64_t off;
+            if constexpr (MULTI) off = decompose(ii, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+            else off = ii * rs0;
+            p[u] = ld_stream<T, VEC>(src + off);
         }
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[u][j] = Op::f(acc[u][j], p[u].v[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p[u].v[j]);
     }
-    // fold the thread's accumulators in a fixed order
-    T v = acc[0][0];
+    for (; i < end; i += G) {
+        int64_t off;
+        if constexpr (MULTI) off = decompose(i, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+        else off = i * rs0;
+        Pack<T, VEC> p = ld_stream<T, VEC>(src + off);
 #pragma unroll
-    for (int u = 0; u < RED_UNROLL; ++u)
+        for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p.v[j]);
+    }
+    // fold the pack lanes, then the group, in a fixed order
+    T v = acc[0];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
-            if (u + j > 0) v = Op::f(v, acc[u][j]);
+    for (int j = 1; j < VEC; ++j) v = Op::f(v, acc[j]);
 
     if (G <= 32) {
-        for (int m = G >> 1; m >= 1; m >>= 1) v = Op::f(v, shfl_xor_t<T, 32>(v, m));
+        for (int m = G >> 1; m >= 1; m >>= 1) v = Op::f(v, shfl_xor_t<T>(v, m));
     } else {
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) v = Op::f(v, shfl_xor_t<T, 32>(v, m));
+        for (int m = 16; m >= 1; m >>= 1) v = Op::f(v, shfl_xor_t<T>(v, m));
         if ((tid & 31) == 0) warp_acc[tid >> 5] = v;
         __syncthreads();
         if (t == 0) {
@@ -192,67 +199,67 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const RedDesc d,
     }
     if (valid && t == 0) {
         if (d.to_partial) partial[(int64_t)blockIdx.y * d.n_out_total + o] = v;
-        else out[off_out] = finalize<T>(v, d, div);
+        else out[off_out] = finalize<T>(v, d.do_div, div);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <class Op, class T, int VEC>
-__global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const RedDesc d, const T *__restrict__ in,
+template <class Op, class T, int VEC, bool MULTI>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_constant__ RedDesc d, const T *__restrict__ in,
                                                                 T *__restrict__ out, T *__restrict__ partial,
                                                                 T div) {
-    extern __shared__ __align__(16) unsigned char red_smem[];
+    extern __shared__ __align__(32) unsigned char red_smem[];
     Pack<T, VEC> *sm = reinterpret_cast<Pack<T, VEC> *>(red_smem);
     const int TC = d.tcol, RW = RED_BLOCK / TC;
     const int tx = threadIdx.x % TC, ty = threadIdx.x / TC;
     const int64_t ntile0 = (d.packs0 + TC - 1) / TC;
     const int64_t tile = blockIdx.x;
-    const int64_t kb = tile / ntile0;          // linear index over kept dims 1..
+    const int64_t kb = tile / ntile0;                    // linear index over kept dims 1..
     const int64_t col = (tile - kb * ntile0) * TC + tx;  // pack index along kept dim 0
     const bool valid = col < d.packs0;
-    int64_t off_in = 0, off_out = 0;
+    int64_t off_out = 0;
+    const T *src = in;
     if (valid) {
-        off_in = col * VEC * d.ks_in[0] + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
-        off_out = col * VEC * d.ks_out[0] + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
+        src += col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
+        off_out = col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
     }
     const int64_t begin = (int64_t)blockIdx.y * d.chunk;
     int64_t end = begin + d.chunk;
     if (end > d.n_items) end = d.n_items;
     if (!valid) end = begin;
 
-    T acc[RED_UNROLL][VEC];
+    T acc[VEC];
 #pragma unroll
-    for (int u = 0; u < RED_UNROLL; ++u)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[u][j] = Op::init();
+    for (int j = 0; j < VEC; ++j) acc[j] = Op::init();
 
-    const int64_t step = (int64_t)RW * RED_UNROLL;
     const int64_t rs0 = d.rs[0];
-    for (int64_t r = begin + ty; r < end; r += step) {
+    int64_t r = begin + ty;
+    for (; r + (int64_t)(RED_UNROLL - 1) * RW < end; r += (int64_t)RW * RED_UNROLL) {
         Pack<T, VEC> p[RED_UNROLL];
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u) {
-            int64_t rr = r + (int64_t)u * RW;
-            if (rr < end) {
-                int64_t off = (d.nr <= 1) ? rr * rs0 : decompose(rr, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
-                p[u] = ld_stream<T, VEC>(in + off_in + off);
-            } else {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) p[u].v[j] = Op::init();
-            }
+            const int64_t rr = r + (int64_t)u * RW;
+            int64_t off;
+            if constexpr (MULTI) off = decompose(rr, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+            else off = rr * rs0;
+            p[u] = ld_stream<T, VEC>(src + off);
         }
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[u][j] = Op::f(acc[u][j], p[u].v[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p[u].v[j]);
+    }
+    for (; r < end; r += RW) {
+        int64_t off;
+        if constexpr (MULTI) off = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+        else off = r * rs0;
+        Pack<T, VEC> p = ld_stream<T, VEC>(src + off);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p.v[j]);
     }
     Pack<T, VEC> v;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        v.v[j] = acc[0][j];
-#pragma unroll
-        for (int u = 1; u < RED_UNROLL; ++u) v.v[j] = Op::f(v.v[j], acc[u][j]);
-    }
+    for (int j = 0; j < VEC; ++j) v.v[j] = acc[j];
     sm[ty * TC + tx] = v;
     __syncthreads();
     if (ty == 0 && valid) {
@@ -263,11 +270,11 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const RedDesc d,
         }
         if (d.to_partial) {
             T *dst = partial + (int64_t)blockIdx.y * d.n_out_total + kb * (d.packs0 * VEC) + col * VEC;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) dst[j] = v.v[j];
+            if (VEC > 1) st_stream<T, VEC>(dst, v);
+            else dst[0] = v.v[0];
         } else {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) v.v[j] = finalize<T>(v.v[j], d, div);
+            for (int j = 0; j < VEC; ++j) v.v[j] = finalize<T>(v.v[j], d.do_div, div);
             if (VEC > 1) st_stream<T, VEC>(out + off_out, v);
             else out[off_out] = v.v[0];
         }
@@ -277,12 +284,6 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const RedDesc d,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int64_t prod(const std::vector<int64_t> &v, size_t from = 0) {
-    int64_t s = 1;
-    for (size_t i = from; i < v.size(); ++i) s *= v[i];
-    return s;
-}
-
 void fill_desc_dims(RedDesc &d, const CanonRed &c) {
     RC_CHECK(c.kshape.size() <= (size_t)KMAXD && c.rshape.size() <= (size_t)KMAXD, RC_ERR_UNIMPLEMENTED,
              "reduction over more than 8 non-mergeable kept or reduced axes");
@@ -306,26 +307,38 @@ template <class T>
 bool aligned_for(const void *p, int vec) { return reinterpret_cast<uintptr_t>(p) % (vec * sizeof(T)) == 0; }
 
 template <class Op, class T>
-void launch_rows(rc_device *dev, RedDesc d, int vec, int64_t sy, const T *in, T *out, T *partial, T div) {
+void launch_rows(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const T *in, T *out, T *partial, T div) {
     int64_t gx = (d.n_out + (RED_BLOCK / d.group) - 1) / (RED_BLOCK / d.group);
     RC_CHECK(gx < (1ll << 31) && sy <= 65535, RC_ERR_UNIMPLEMENTED, "reduction grid too large");
     dim3 grid((unsigned)gx, (unsigned)sy);
-    constexpr int V = 16 / sizeof(T);
-    if (vec > 1) reduce_rows_kernel<Op, T, V><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
-    else reduce_rows_kernel<Op, T, 1><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
+    constexpr int V = 32 / sizeof(T);
+    const bool multi = d.nr > 1;
+    if (vec > 1) {
+        if (multi) reduce_rows_kernel<Op, T, V, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
+        else reduce_rows_kernel<Op, T, V, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
+    } else {
+        if (multi) reduce_rows_kernel<Op, T, 1, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
+        else reduce_rows_kernel<Op, T, 1, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
+    }
     after_launch(dev, "reduce_rows_kernel");
 }
 
 template <class Op, class T>
-void launch_cols(rc_device *dev, RedDesc d, int vec, int64_t sy, const T *in, T *out, T *partial, T div) {
+void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const T *in, T *out, T *partial, T div) {
     int64_t ntile0 = (d.packs0 + d.tcol - 1) / d.tcol;
     int64_t gx = ntile0 * d.n_out;
     RC_CHECK(gx < (1ll << 31) && sy <= 65535, RC_ERR_UNIMPLEMENTED, "reduction grid too large");
     dim3 grid((unsigned)gx, (unsigned)sy);
-    constexpr int V = 16 / sizeof(T);
+    constexpr int V = 32 / sizeof(T);
     size_t smem = (size_t)RED_BLOCK * sizeof(T) * (vec > 1 ? V : 1);
-    if (vec > 1) reduce_cols_kernel<Op, T, V><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
-    else reduce_cols_kernel<Op, T, 1><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
+    const bool multi = d.nr > 1;
+    if (vec > 1) {
+        if (multi) reduce_cols_kernel<Op, T, V, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
+        else reduce_cols_kernel<Op, T, V, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
+    } else {
+        if (multi) reduce_cols_kernel<Op, T, 1, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
+        else reduce_cols_kernel<Op, T, 1, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
+    }
     after_launch(dev, "reduce_cols_kernel");
 }
 
@@ -339,8 +352,9 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     T *out = static_cast<T *>(out_v) + c.base_out;
     T div = (T)1;
     if (mean) div = (T)mean_count;  // T::from_usize(n) (auto_impl/reduction.rs:181,199)
-    constexpr int V = 16 / sizeof(T);
+    constexpr int V = 32 / sizeof(T);
     const int64_t n_out = c.n_out(), n_red = c.n_red();
+    // 2 resident CTAs per SM keep 2 x 256 threads x 8 x 32 B = 128 KB in flight; aim for >= 4 waves of work
     const int64_t target_ctas = (int64_t)dev->sm_count * 8;
 
     RedDesc d;
@@ -355,7 +369,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
 
     if (!red_contig && kept_contig && n_red > 0) {
         // ---------------- column kernel ----------------
-        bool vec_ok = V > 1 && d.kshape[0] % V == 0 && aligned_for<T>(in, V) && aligned_for<T>(out, V);
+        bool vec_ok = d.kshape[0] % V == 0 && aligned_for<T>(in, V) && aligned_for<T>(out, V);
         for (int i = 1; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0 && d.ks_out[i] % V == 0;
         for (int i = 0; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
         const int vec = vec_ok ? V : 1;
@@ -366,7 +380,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         if (n_red >= (1ll << 31) || d.n_out >= (1ll << 31)) d.big = 1;
         const int rw = RED_BLOCK / d.tcol;
         int64_t base_ctas = ((d.packs0 + d.tcol - 1) / d.tcol) * d.n_out;
-        int64_t S = std::min<int64_t>((2 * target_ctas + base_ctas - 1) / base_ctas,
+        int64_t S = std::min<int64_t>((target_ctas + base_ctas - 1) / base_ctas,
                                       std::max<int64_t>(1, n_red / ((int64_t)rw * RED_UNROLL * 2)));
         S = std::max<int64_t>(1, std::min<int64_t>(S, 1024));
         d.chunk = (n_red + S - 1) / S;
@@ -390,7 +404,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         for (int i = 0; i < e.nk; ++i) { e.ks_in[i] = acc; acc *= e.kshape[i]; }
         e.n_items = S;
         e.chunk = S;
-        bool vec2 = vec_ok && (n_out % V == 0) && aligned_for<T>(partial, V);
+        const bool vec2 = vec_ok && (n_out % V == 0) && aligned_for<T>(partial, V);
         const int v2 = vec2 ? V : 1;
         e.packs0 = e.kshape[0] / v2;
         e.tcol = (int)std::min<int64_t>(32, pow2_ceil(e.packs0));
@@ -399,7 +413,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     }
 
     // ---------------- row kernel (contiguous or generic reduced space) ----------------
-    bool vec_ok = V > 1 && d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_for<T>(in, V);
+    bool vec_ok = d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_for<T>(in, V);
     for (int i = 0; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0;
     for (int i = 1; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
     const int vec = vec_ok ? V : 1;
@@ -416,7 +430,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     }
     d.n_out = n_out;
     d.n_items = n_red / vec;
-    if (d.n_items >= (1ll << 31)) d.big = (d.nr > 1) ? 1 : d.big;
+    if (d.n_items >= (1ll << 31) && d.nr > 1) d.big = 1;
     d.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, d.n_items / RED_UNROLL))));
     int64_t base_ctas = (n_out + (RED_BLOCK / d.group) - 1) / (RED_BLOCK / d.group);
     int64_t S = 1;
@@ -447,7 +461,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     for (int i = 0; i < e.nk; ++i) { e.ks_in[i] = acc; acc *= e.kshape[i]; }
     e.n_items = S;
     e.chunk = S;
-    e.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, S / RED_UNROLL))));
+    e.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, S / 2))));
     launch_rows<Op, T>(dev, e, 1, 1, partial, out, (T *)nullptr, div);
 }
 

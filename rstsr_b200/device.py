@@ -1,0 +1,415 @@
+"""`DeviceCuda`: host-side mirror of the reference's device-trait surface over the C ABI.
+
+Method names and argument order follow the reference traits (paths inside RESTGroup/rstsr v0.7.10) so the parity
+tests read like the reference's own:
+
+    DeviceBaseAPI / DeviceStorageAPI / DeviceCreation*API   rstsr-core/src/storage/{device,creation}.rs
+    OpAssignAPI, OpAssignArbitaryAPI                        rstsr-core/src/operators/assignment.rs:5-53
+    Op{Add..Shr}API, Op*AssignAPI, OpL/RConsume*API          rstsr-core/src/operators/ops/op_{ternary,binary}_arithmetic.rs
+    unary / binary-function traits                          rstsr-core/src/operators/ops/op_{binary,ternary}_common.rs
+    Op{Sum,Prod,Max,Min,Mean}API                            rstsr-core/src/operators/reduction.rs:3-33
+
+Everything numerical happens in librstsr_cuda.so (hand-written CUDA for sm_100a); this file only marshals
+arguments.  It never touches `oracle/` and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import CLayout, RstsrCudaError, byref, check
+
+_NP_TO_DT = {np.dtype(np.bool_): _ffi.BOOL, np.dtype(np.int8): _ffi.I8, np.dtype(np.int16): _ffi.I16,
+             np.dtype(np.int32): _ffi.I32, np.dtype(np.int64): _ffi.I64, np.dtype(np.uint8): _ffi.U8,
+             np.dtype(np.uint16): _ffi.U16, np.dtype(np.uint32): _ffi.U32, np.dtype(np.uint64): _ffi.U64,
+             np.dtype(np.float32): _ffi.F32, np.dtype(np.float64): _ffi.F64}
+_DT_TO_NP = {v: k for k, v in _NP_TO_DT.items()}
+
+
+def dtype_code(dt) -> int:
+    return _NP_TO_DT[np.dtype(dt)]
+
+
+def dtype_np(code: int) -> np.dtype:
+    return _DT_TO_NP[code]
+
+
+@dataclass(frozen=True)
+class Layout:
+    """Layout<IxD> (rstsr-common/src/layout/layoutbase.rs:15-23): element strides, element offset."""
+    shape: Tuple[int, ...]
+    stride: Tuple[int, ...]
+    offset: int = 0
+
+    def __post_init__(self):
+        object.__setattr__(self, "shape", tuple(int(x) for x in self.shape))
+        object.__setattr__(self, "stride", tuple(int(x) for x in self.stride))
+        object.__setattr__(self, "offset", int(self.offset))
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def size(self) -> int:
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+    def to_c(self) -> CLayout:
+        if len(self.shape) != len(self.stride) or len(self.shape) > _ffi.RC_MAX_NDIM:
+            raise RstsrCudaError(3, "invalid layout rank")
+        c = CLayout()
+        c.ndim = len(self.shape)
+        for i, (d, s) in enumerate(zip(self.shape, self.stride)):
+            c.shape[i] = d
+            c.stride[i] = s
+        c.offset = self.offset
+        return c
+
+    @staticmethod
+    def from_c(c: CLayout) -> "Layout":
+        n = c.ndim
+        return Layout(tuple(c.shape[i] for i in range(n)), tuple(c.stride[i] for i in range(n)), c.offset)
+
+    # ---- host-side layout algebra, evaluated by the library (reference-identical by contract) ----
+    def bounds_index(self) -> Tuple[int, int]:
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        check(_ffi.lib().rc_layout_bounds_index(byref(self.to_c()), byref(lo), byref(hi)))
+        return lo.value, hi.value
+
+    def check(self) -> "Layout":
+        check(_ffi.lib().rc_layout_check(byref(self.to_c())))
+        return self
+
+    def c_contig(self) -> bool:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_layout_c_contig(byref(self.to_c()), byref(out)))
+        return bool(out.value)
+
+    def f_contig(self) -> bool:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_layout_f_contig(byref(self.to_c()), byref(out)))
+        return bool(out.value)
+
+    def same_as(self, other: "Layout") -> bool:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_layout_equal(byref(self.to_c()), byref(other.to_c()), byref(out)))
+        return bool(out.value)
+
+    @staticmethod
+    def contig(shape: Sequence[int], order: int, offset: int = 0) -> "Layout":
+        arr = (ctypes.c_int64 * max(len(shape), 1))(*[int(x) for x in shape])
+        out = CLayout()
+        check(_ffi.lib().rc_layout_new_contig(arr, len(shape), order, offset, byref(out)))
+        return Layout.from_c(out)
+
+
+def broadcast_layout(la: Layout, lb: Layout, order: int) -> Tuple[Layout, Layout]:
+    oa, ob = CLayout(), CLayout()
+    check(_ffi.lib().rc_layout_broadcast(byref(la.to_c()), byref(lb.to_c()), order, byref(oa), byref(ob)))
+    return Layout.from_c(oa), Layout.from_c(ob)
+
+
+def layout_for_binary_op(la: Layout, lb: Layout, order: int) -> Layout:
+    out = CLayout()
+    check(_ffi.lib().rc_layout_for_binary_op(byref(la.to_c()), byref(lb.to_c()), order, byref(out)))
+    return Layout.from_c(out)
+
+
+def layout_for_array_copy(la: Layout, iter_order: int = _ffi.ITER_K, default_order: int = _ffi.ROW_MAJOR) -> Layout:
+    out = CLayout()
+    check(_ffi.lib().rc_layout_for_array_copy(byref(la.to_c()), iter_order, default_order, byref(out)))
+    return Layout.from_c(out)
+
+
+def layout_for_reduce(la: Layout, axes: Sequence[int]) -> Layout:
+    arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])
+    out = CLayout()
+    check(_ffi.lib().rc_layout_for_reduce(byref(la.to_c()), arr, len(axes), byref(out)))
+    return Layout.from_c(out)
+
+
+def layout_reshapeable(la: Layout, shape: Sequence[int], order: int) -> Optional[Layout]:
+    arr = (ctypes.c_int64 * max(len(shape), 1))(*[int(x) for x in shape])
+    ok = ctypes.c_int()
+    out = CLayout()
+    check(_ffi.lib().rc_layout_reshapeable(byref(la.to_c()), arr, len(shape), order, byref(ok), byref(out)))
+    return Layout.from_c(out) if ok.value else None
+
+
+class CudaRaw:
+    """Device buffer: the `Raw` of DeviceRawAPI (Vec<T> on the CPU devices).  Drop = free."""
+
+    def __init__(self, device: "DeviceCuda", ptr: int, length: int, dtype, owned: bool = True):
+        self.device = device
+        self.ptr = int(ptr)
+        self.len = int(length)
+        self.dtype = np.dtype(dtype)
+        self._owned = owned
+
+    @property
+    def nbytes(self) -> int:
+        return self.len * self.dtype.itemsize
+
+    def free(self):
+        if self._owned and self.ptr and self.device._handle:
+            _ffi.lib().rc_free(self.device._handle, self.ptr)
+        self.ptr = 0
+        self._owned = False
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def clone(self) -> "CudaRaw":
+        out = self.device.uninit_impl(self.dtype, self.len)
+        check(_ffi.lib().rc_memcpy_d2d(self.device._handle, out.ptr, self.ptr, self.nbytes))
+        return out
+
+
+class DeviceCuda:
+    """A CUDA device: {ordinal, default_order, stream} (cf. DeviceFaer: {pool, default_order},
+    rstsr-core/src/device_faer/device.rs:5-60)."""
+
+    def __init__(self, ordinal: int = 0, default_order: int = _ffi.ROW_MAJOR, stream: Optional[int] = None):
+        self._handle = None
+        h = ctypes.c_void_p()
+        if stream is None:
+            check(_ffi.lib().rc_device_create(ordinal, default_order, byref(h)))
+        else:
+            check(_ffi.lib().rc_device_create_on_stream(ordinal, default_order, ctypes.c_void_p(stream), byref(h)))
+        self._handle = h
+        self.ordinal = ordinal
+
+    def close(self):
+        if self._handle:
+            _ffi.lib().rc_device_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- DeviceBaseAPI ----
+    def default_order(self) -> int:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_device_default_order(self._handle, byref(out)))
+        return out.value
+
+    def set_default_order(self, order: int):
+        check(_ffi.lib().rc_device_set_default_order(self._handle, order))
+
+    def same_device(self, other: "DeviceCuda") -> bool:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_device_same_device(self._handle, other._handle, byref(out)))
+        return bool(out.value)
+
+    def synchronize(self):
+        check(_ffi.lib().rc_device_synchronize(self._handle))
+
+    def launch_count(self) -> int:
+        out = ctypes.c_uint64()
+        check(_ffi.lib().rc_device_launch_count(self._handle, byref(out)))
+        return out.value
+
+    def stream(self) -> int:
+        out = ctypes.c_void_p()
+        check(_ffi.lib().rc_device_stream(self._handle, byref(out)))
+        return out.value or 0
+
+    # ---- DeviceCreationAnyAPI / NumAPI / DeviceStorageAPI ----
+    def uninit_impl(self, dtype, length: int) -> CudaRaw:
+        p = ctypes.c_void_p()
+        dt = np.dtype(dtype)
+        check(_ffi.lib().rc_malloc(self._handle, int(length) * dt.itemsize, byref(p)))
+        return CudaRaw(self, p.value, length, dt)
+
+    empty_impl = uninit_impl
+
+    def zeros_impl(self, dtype, length: int) -> CudaRaw:
+        raw = self.uninit_impl(dtype, length)
+        check(_ffi.lib().rc_memset(self._handle, raw.ptr, 0, raw.nbytes))
+        return raw
+
+    def full_impl(self, dtype, length: int, value) -> CudaRaw:
+        raw = self.uninit_impl(dtype, length)
+        self.fill(raw, Layout((length,), (1,), 0), value)
+        return raw
+
+    def ones_impl(self, dtype, length: int) -> CudaRaw:
+        return self.full_impl(dtype, length, 1)
+
+    def outof_cpu_vec(self, vec: np.ndarray) -> CudaRaw:
+        vec = np.ascontiguousarray(vec).reshape(-1)
+        raw = self.uninit_impl(vec.dtype, vec.size)
+        check(_ffi.lib().rc_memcpy_h2d(self._handle, raw.ptr, vec.ctypes.data, vec.nbytes))
+        self.synchronize()  # `vec` may be a temporary
+        return raw
+
+    from_cpu_vec = outof_cpu_vec
+
+    def to_cpu_vec(self, raw: CudaRaw) -> np.ndarray:
+        out = np.empty(raw.len, dtype=raw.dtype)
+        check(_ffi.lib().rc_memcpy_d2h(self._handle, out.ctypes.data, raw.ptr, raw.nbytes))
+        return out
+
+    def wrap(self, ptr: int, length: int, dtype) -> CudaRaw:
+        """Borrow device memory owned by someone else (e.g. a torch tensor's data_ptr())."""
+        return CudaRaw(self, ptr, length, dtype, owned=False)
+
+    def get_index(self, raw: CudaRaw, index: int):
+        out = np.empty(1, dtype=raw.dtype)
+        check(_ffi.lib().rc_get_index(self._handle, dtype_code(raw.dtype), raw.ptr, index, out.ctypes.data))
+        return out[0]
+
+    def set_index(self, raw: CudaRaw, index: int, value):
+        v = np.array([value], dtype=raw.dtype)
+        check(_ffi.lib().rc_set_index(self._handle, dtype_code(raw.dtype), raw.ptr, index, v.ctypes.data))
+
+    # ---- OpAssignAPI / OpAssignArbitaryAPI ----
+    def assign(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout):
+        check(_ffi.lib().rc_assign(self._handle, dtype_code(c.dtype), c.ptr, byref(lc.to_c()), dtype_code(a.dtype), a.ptr,
+                                   byref(la.to_c())))
+
+    assign_uninit = assign
+
+    def assign_arbitary(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout):
+        check(_ffi.lib().rc_assign_arbitary(self._handle, dtype_code(c.dtype), c.ptr, byref(lc.to_c()),
+                                            dtype_code(a.dtype), a.ptr, byref(la.to_c())))
+
+    assign_arbitary_uninit = assign_arbitary
+
+    def fill(self, c: CudaRaw, lc: Layout, value):
+        v = np.array([value])
+        if v.dtype not in _NP_TO_DT:
+            v = v.astype(c.dtype)
+        check(_ffi.lib().rc_fill(self._handle, dtype_code(c.dtype), c.ptr, byref(lc.to_c()), dtype_code(v.dtype),
+                                 v.ctypes.data))
+
+    # ---- elementwise ----
+    @staticmethod
+    def _scalar(value, dtype) -> np.ndarray:
+        return np.array([value]).astype(dtype)
+
+    def op_mutc_refa_refb(self, op: str, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout):
+        check(_ffi.lib().rc_op_mutc_refa_refb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), c.ptr, byref(lc.to_c()),
+                                              a.ptr, byref(la.to_c()), b.ptr, byref(lb.to_c())))
+
+    def op_mutc_refa_numb(self, op: str, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b):
+        s = self._scalar(b, a.dtype)
+        check(_ffi.lib().rc_op_mutc_refa_numb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), c.ptr, byref(lc.to_c()),
+                                              a.ptr, byref(la.to_c()), s.ctypes.data))
+
+    def op_mutc_numa_refb(self, op: str, c: CudaRaw, lc: Layout, a, b: CudaRaw, lb: Layout):
+        s = self._scalar(a, b.dtype)
+        check(_ffi.lib().rc_op_mutc_numa_refb(self._handle, _ffi.BINOPS[op], dtype_code(b.dtype), c.ptr, byref(lc.to_c()),
+                                              s.ctypes.data, b.ptr, byref(lb.to_c())))
+
+    def op_muta_refb(self, op: str, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, reverse: bool = False):
+        """a = a o b (Op*AssignAPI / OpLConsume*API); reverse: a = b o a (OpRConsume*API)."""
+        check(_ffi.lib().rc_op_muta_refb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
+                                         b.ptr, byref(lb.to_c()), 1 if reverse else 0))
+
+    def op_muta_numb(self, op: str, a: CudaRaw, la: Layout, b, reverse: bool = False):
+        s = self._scalar(b, a.dtype)
+        check(_ffi.lib().rc_op_muta_numb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
+                                         s.ctypes.data, 1 if reverse else 0))
+
+    def unary_muta_refb(self, op: str, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout):
+        check(_ffi.lib().rc_unary_muta_refb(self._handle, _ffi.UNOPS[op], dtype_code(b.dtype), a.ptr, byref(la.to_c()),
+                                            b.ptr, byref(lb.to_c())))
+
+    def unary_muta(self, op: str, a: CudaRaw, la: Layout):
+        check(_ffi.lib().rc_unary_muta(self._handle, _ffi.UNOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c())))
+
+    @staticmethod
+    def binop_out_dtype(op: str, dtype) -> np.dtype:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_binop_out_dtype(_ffi.BINOPS[op], dtype_code(dtype), byref(out)))
+        return dtype_np(out.value)
+
+    @staticmethod
+    def unop_out_dtype(op: str, dtype) -> np.dtype:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_unop_out_dtype(_ffi.UNOPS[op], dtype_code(dtype), byref(out)))
+        return dtype_np(out.value)
+
+    # ---- reductions ----
+    def reduce_all(self, op: str, a: CudaRaw, la: Layout):
+        out = np.empty(1, dtype=a.dtype)
+        check(_ffi.lib().rc_reduce_all(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
+                                       out.ctypes.data))
+        return out[0]
+
+    def reduce_all_device(self, op: str, a: CudaRaw, la: Layout, out: CudaRaw):
+        check(_ffi.lib().rc_reduce_all_device(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr,
+                                              byref(la.to_c()), out.ptr))
+
+    def reduce_axes(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int]) -> Tuple[CudaRaw, Layout]:
+        arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])
+        p = ctypes.c_void_p()
+        lo = CLayout()
+        check(_ffi.lib().rc_reduce_axes(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()), arr,
+                                        len(axes), byref(p), byref(lo)))
+        layout = Layout.from_c(lo)
+        return CudaRaw(self, p.value, max(layout.size, 1), a.dtype), layout
+
+    def reduce_axes_into(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int], out: CudaRaw, lo: Layout):
+        arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])
+        check(_ffi.lib().rc_reduce_axes_into(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
+                                             arr, len(axes), out.ptr, byref(lo.to_c())))
+
+    # trait-named conveniences: sum_all / sum_axes / ... (operators/reduction.rs:26-32)
+    def sum_all(self, a, la): return self.reduce_all("sum", a, la)
+    def prod_all(self, a, la): return self.reduce_all("prod", a, la)
+    def max_all(self, a, la): return self.reduce_all("max", a, la)
+    def min_all(self, a, la): return self.reduce_all("min", a, la)
+    def mean_all(self, a, la): return self.reduce_all("mean", a, la)
+    def sum_axes(self, a, la, axes): return self.reduce_axes("sum", a, la, axes)
+    def prod_axes(self, a, la, axes): return self.reduce_axes("prod", a, la, axes)
+    def max_axes(self, a, la, axes): return self.reduce_axes("max", a, la, axes)
+    def min_axes(self, a, la, axes): return self.reduce_axes("min", a, la, axes)
+    def mean_axes(self, a, la, axes): return self.reduce_axes("mean", a, la, axes)
+
+
+class Comm:
+    """NCCL communicator for cross-shard reductions: one rank per process / GPU."""
+
+    def __init__(self, device: DeviceCuda, nranks: int, rank: int, unique_id: bytes):
+        self.device = device
+        self.nranks, self.rank = nranks, rank
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(_ffi.lib().rc_comm_init_rank(device._handle, nranks, rank, buf, byref(h)))
+        self._handle = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * 128)()
+        check(_ffi.lib().rc_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def all_reduce(self, op: str, buf: CudaRaw, count: Optional[int] = None):
+        check(_ffi.lib().rc_comm_all_reduce(self._handle, _ffi.REDOPS[op], dtype_code(buf.dtype), buf.ptr,
+                                            buf.len if count is None else count))
+
+    def reduce_all_sharded(self, op: str, a: CudaRaw, la: Layout, n_global: int):
+        out = np.empty(1, dtype=a.dtype)
+        check(_ffi.lib().rc_reduce_all_sharded(self.device._handle, self._handle, _ffi.REDOPS[op], dtype_code(a.dtype),
+                                               a.ptr, byref(la.to_c()), n_global, out.ctypes.data))
+        return out[0]
+
+    def close(self):
+        if self._handle:
+            _ffi.lib().rc_comm_destroy(self._handle)
+            self._handle = None

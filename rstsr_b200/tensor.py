@@ -1,0 +1,370 @@
+"""A thin `Tensor` over DeviceCuda -- just enough of rstsr's L4 tensor API to drive the device path the way the
+reference's callers do (`&a + &b`, `a.to_contig(order)`, `a.sum_axes(ax)`, ...), so tests read like the reference's.
+
+Each method states the reference caller it mirrors; all of them do what the reference does on the host
+(broadcast, choose the output layout, allocate) and then make exactly ONE device call.  Host-side decisions are
+evaluated by the C++ layout algebra inside librstsr_cuda.so (via rstsr_b200.device helpers), never by `oracle/`.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _ffi
+from .device import (CudaRaw, DeviceCuda, Layout, broadcast_layout, layout_for_array_copy, layout_for_binary_op,
+                     layout_reshapeable)
+
+ROW_MAJOR, COL_MAJOR = _ffi.ROW_MAJOR, _ffi.COL_MAJOR
+_FUNC_OPS = {"maximum", "minimum", "floor_divide", "pow", "atan2", "copysign", "hypot", "logaddexp", "nextafter",
+             "eq", "ne", "lt", "le", "gt", "ge"}
+
+
+class Tensor:
+    """(storage, layout) pair: TensorBase<Storage<R, T, B>, D> (rstsr-core/src/tensorbase.rs:5-25)."""
+
+    def __init__(self, raw: CudaRaw, layout: Layout, owned: bool = True):
+        self.raw = raw
+        self.layout = layout
+        self.owned = owned  # Tensor (owns its buffer) vs TensorView
+
+    # ---- basic properties ----
+    @property
+    def device(self) -> DeviceCuda:
+        return self.raw.device
+
+    @property
+    def dtype(self) -> np.dtype:
+        return self.raw.dtype
+
+    @property
+    def shape(self) -> Tuple[int, ...]:
+        return self.layout.shape
+
+    @property
+    def stride(self) -> Tuple[int, ...]:
+        return self.layout.stride
+
+    @property
+    def ndim(self) -> int:
+        return self.layout.ndim
+
+    @property
+    def size(self) -> int:
+        return self.layout.size
+
+    def view(self) -> "Tensor":
+        return Tensor(self.raw, self.layout, owned=False)
+
+    def _with(self, layout: Layout) -> "Tensor":
+        return Tensor(self.raw, layout, owned=False)
+
+    # ---- host transfer ----
+    def to_numpy(self) -> np.ndarray:
+        """Download the whole storage and materialise this view (C-contiguous numpy array)."""
+        host = self.device.to_cpu_vec(self.raw)
+        l = self.layout
+        if l.size == 0:
+            return np.zeros(l.shape, dtype=self.dtype)
+        item = host.dtype.itemsize
+        v = np.lib.stride_tricks.as_strided(host[l.offset:], shape=l.shape, strides=tuple(s * item for s in l.stride),
+                                            writeable=False)
+        return np.array(v)
+
+    def to_vec(self) -> np.ndarray:
+        """to_vec (1-D only; rstsr-core/src/tensor/ownership_conversion.rs:177-187)."""
+        if self.ndim != 1:
+            raise _ffi.RstsrCudaError(3, "to_vec is only defined for 1-D tensors")
+        return self.to_numpy()
+
+    def to_scalar(self):
+        if self.size != 1:
+            raise _ffi.RstsrCudaError(3, "to_scalar needs exactly one element")
+        return self.device.get_index(self.raw, self.layout.offset)
+
+    # ---- views: no data movement (rstsr-core/src/tensor/manipulation/{transpose,...}.rs) ----
+    def transpose(self, axes: Optional[Sequence[int]] = None) -> "Tensor":
+        n = self.ndim
+        if axes is None:
+            axes = list(range(n))[::-1]
+        ax = [a + n if a < 0 else a for a in axes]
+        if sorted(ax) != list(range(n)):
+            raise _ffi.RstsrCudaError(3, "invalid permutation")
+        l = self.layout
+        return self._with(Layout(tuple(l.shape[a] for a in ax), tuple(l.stride[a] for a in ax), l.offset))
+
+    into_transpose = transpose
+    permute_dims = transpose
+
+    def swapaxes(self, a1: int, a2: int) -> "Tensor":
+        ax = list(range(self.ndim))
+        ax[a1], ax[a2] = ax[a2], ax[a1]
+        return self.transpose(ax)
+
+    into_swapaxes = swapaxes
+
+    def reverse_axes(self) -> "Tensor":
+        return self.transpose(None)
+
+    def flip(self, axis: int) -> "Tensor":
+        return self[tuple(slice(None, None, -1) if i == (axis % self.ndim) else slice(None) for i in range(self.ndim))]
+
+    def expand_dims(self, axis: int) -> "Tensor":
+        l = self.layout
+        if axis < 0:
+            axis += l.ndim + 1
+        return self._with(Layout(l.shape[:axis] + (1,) + l.shape[axis:], l.stride[:axis] + (1,) + l.stride[axis:], l.offset))
+
+    def broadcast_to(self, shape: Sequence[int]) -> "Tensor":
+        target = Layout.contig(shape, self.device.default_order())
+        la_b, _ = broadcast_layout(self.layout, target, self.device.default_order())
+        if la_b.shape != tuple(shape):
+            raise _ffi.RstsrCudaError(3, "Broadcasting failed.")
+        return self._with(la_b)
+
+    def __getitem__(self, key) -> "Tensor":
+        """`.i(...)` with ints, slices, None and Ellipsis, NumPy slice semantics for in-range bounds."""
+        if not isinstance(key, tuple):
+            key = (key,)
+        n_real = sum(1 for k in key if k is not None and k is not Ellipsis)
+        if Ellipsis in key:
+            i = key.index(Ellipsis)
+            key = key[:i] + (slice(None),) * (self.ndim - n_real) + key[i + 1:]
+        shape, stride, offset = [], [], self.layout.offset
+        axis = 0
+        for k in key:
+            if k is None:
+                shape.append(1)
+                stride.append(1)
+                continue
+            d, s = self.layout.shape[axis], self.layout.stride[axis]
+            if isinstance(k, slice):
+                start, stop, step = k.indices(d)
+                length = len(range(start, stop, step))
+                if length > 0:
+                    offset += start * s
+                shape.append(length)
+                stride.append(s * step)
+            else:
+                k = int(k)
+                if k < 0:
+                    k += d
+                if not 0 <= k < d:
+                    raise _ffi.RstsrCudaError(9, "index out of bounds")
+                offset += k * s
+            axis += 1
+        while axis < self.ndim:
+            shape.append(self.layout.shape[axis])
+            stride.append(self.layout.stride[axis])
+            axis += 1
+        return self._with(Layout(tuple(shape), tuple(stride), offset))
+
+    i = __getitem__
+
+    # ---- copies ----
+    def to_layout(self, layout: Layout) -> "Tensor":
+        """change_layout_f (rstsr-core/src/tensor/manipulation/to_layout.rs:8-38)."""
+        if layout.size != self.layout.size:
+            raise _ffi.RstsrCudaError(3, "size mismatch")
+        if layout.same_as(self.layout):
+            return self.view()
+        dev = self.device
+        raw = dev.uninit_impl(self.dtype, layout.bounds_index()[1])
+        dev.assign_arbitary_uninit(raw, layout, self.raw, self.layout)
+        return Tensor(raw, layout)
+
+    def to_contig(self, order: Optional[int] = None) -> "Tensor":
+        """to_contig / change_contig_f (manipulation/to_contig.rs:8-23,81-103)."""
+        order = self.device.default_order() if order is None else order
+        return self.to_layout(Layout.contig(self.shape, order))
+
+    def to_owned(self) -> "Tensor":
+        """asarray((&t, K)) (rstsr-core/src/tensor/asarray.rs:321-341): same-shape copy into a K-order layout."""
+        dev = self.device
+        lc = layout_for_array_copy(self.layout, _ffi.ITER_K, dev.default_order())
+        raw = dev.uninit_impl(self.dtype, lc.bounds_index()[1])
+        dev.assign_uninit(raw, lc, self.raw, self.layout)
+        return Tensor(raw, lc)
+
+    def astype(self, dtype) -> "Tensor":
+        dev = self.device
+        lc = layout_for_array_copy(self.layout, _ffi.ITER_K, dev.default_order())
+        raw = dev.uninit_impl(dtype, lc.bounds_index()[1])
+        dev.assign_uninit(raw, lc, self.raw, self.layout)
+        return Tensor(raw, lc)
+
+    def reshape(self, shape: Sequence[int], order: Optional[int] = None) -> "Tensor":
+        """change_shape_with_args_f (manipulation/reshape.rs:113-166): view if possible, else copy."""
+        dev = self.device
+        order = dev.default_order() if order is None else order
+        shape = list(shape) if not isinstance(shape, int) else [shape]
+        if -1 in shape:
+            rest = 1
+            for v in shape:
+                if v != -1:
+                    rest *= v
+            shape[shape.index(-1)] = self.size // rest if rest else 0
+        view = layout_reshapeable(self.layout, shape, order)
+        if view is not None:
+            return self._with(view)
+        target = Layout.contig(shape, order)
+        raw = dev.uninit_impl(self.dtype, max(target.size, 1))
+        saved = dev.default_order()
+        dev.set_default_order(order)  # reshape.rs:155-162: pairing order = the requested order
+        try:
+            dev.assign_arbitary_uninit(raw, target, self.raw, self.layout)
+        finally:
+            dev.set_default_order(saved)
+        return Tensor(raw, target)
+
+    into_shape = reshape
+
+    def assign(self, other: Union["Tensor", int, float]):
+        """a.assign(&b) / a.fill(v) (rstsr-core/src/tensor/assignment.rs:26-52,111-124)."""
+        dev = self.device
+        if not isinstance(other, Tensor):
+            dev.fill(self.raw, self.layout, other)
+            return self
+        la, lb = broadcast_layout(self.layout, other.layout, dev.default_order())
+        if la.shape != self.layout.shape:
+            raise _ffi.RstsrCudaError(3, "cannot broadcast to the assigned tensor")
+        dev.assign(self.raw, la, other.raw, lb)
+        return self
+
+    fill = assign
+
+    # ---- elementwise ----
+    def _binary(self, op: str, other, reverse: bool = False) -> "Tensor":
+        dev = self.device
+        order = dev.default_order()
+        out_dtype = dev.binop_out_dtype(op, self.dtype)
+        if isinstance(other, Tensor):
+            a, b = (other, self) if reverse else (self, other)
+            if not a.device.same_device(b.device):
+                raise _ffi.RstsrCudaError(5, "DeviceMismatch")
+            la_b, lb_b = broadcast_layout(a.layout, b.layout, order)
+            if op in _FUNC_OPS:  # op_binary_common.rs:79-93
+                l1 = layout_for_array_copy(la_b, _ffi.ITER_K, order)
+                l2 = layout_for_array_copy(lb_b, _ffi.ITER_K, order)
+                lc = l1 if l1.same_as(l2) else Layout.contig(la_b.shape, order)
+            else:  # op_binary_arithmetic.rs:170-213
+                lc = layout_for_binary_op(la_b, lb_b, order)
+            raw = dev.uninit_impl(out_dtype, lc.bounds_index()[1])
+            dev.op_mutc_refa_refb(op, raw, lc, a.raw, la_b, b.raw, lb_b)
+            return Tensor(raw, lc)
+        # scalar operand (op_binary_arithmetic.rs:676-677, 746): layout_for_array_copy(K)
+        lc = layout_for_array_copy(self.layout, _ffi.ITER_K, order)
+        raw = dev.uninit_impl(out_dtype, lc.bounds_index()[1])
+        if reverse:
+            dev.op_mutc_numa_refb(op, raw, lc, other, self.raw, self.layout)
+        else:
+            dev.op_mutc_refa_numb(op, raw, lc, self.raw, self.layout, other)
+        return Tensor(raw, lc)
+
+    def _inplace(self, op: str, other) -> "Tensor":
+        dev = self.device
+        if isinstance(other, Tensor):
+            la, lb = broadcast_layout(self.layout, other.layout, dev.default_order())
+            if la.shape != self.layout.shape or la.stride != self.layout.stride:
+                raise _ffi.RstsrCudaError(3, "cannot broadcast to the in-place operand")
+            dev.op_muta_refb(op, self.raw, la, other.raw, lb)
+        else:
+            dev.op_muta_numb(op, self.raw, self.layout, other)
+        return self
+
+    def __add__(self, o): return self._binary("add", o)
+    def __radd__(self, o): return self._binary("add", o, reverse=True)
+    def __sub__(self, o): return self._binary("sub", o)
+    def __rsub__(self, o): return self._binary("sub", o, reverse=True)
+    def __mul__(self, o): return self._binary("mul", o)
+    def __rmul__(self, o): return self._binary("mul", o, reverse=True)
+    def __truediv__(self, o): return self._binary("div", o)
+    def __rtruediv__(self, o): return self._binary("div", o, reverse=True)
+    def __mod__(self, o): return self._binary("rem", o)
+    def __or__(self, o): return self._binary("bitor", o)
+    def __and__(self, o): return self._binary("bitand", o)
+    def __xor__(self, o): return self._binary("bitxor", o)
+    def __lshift__(self, o): return self._binary("shl", o)
+    def __rshift__(self, o): return self._binary("shr", o)
+    def __iadd__(self, o): return self._inplace("add", o)
+    def __isub__(self, o): return self._inplace("sub", o)
+    def __imul__(self, o): return self._inplace("mul", o)
+    def __itruediv__(self, o): return self._inplace("div", o)
+
+    def binary(self, op: str, other) -> "Tensor":
+        return self._binary(op, other)
+
+    def _unary(self, op: str) -> "Tensor":
+        dev = self.device
+        la = layout_for_array_copy(self.layout, _ffi.ITER_K, dev.default_order())  # op_unary_common.rs:150-153
+        raw = dev.uninit_impl(dev.unop_out_dtype(op, self.dtype), la.bounds_index()[1])
+        dev.unary_muta_refb(op, raw, la, self.raw, self.layout)
+        return Tensor(raw, la)
+
+    def unary(self, op: str) -> "Tensor":
+        return self._unary(op)
+
+    def unary_inplace(self, op: str) -> "Tensor":
+        self.device.unary_muta(op, self.raw, self.layout)
+        return self
+
+    def __neg__(self): return self._unary("neg")
+    def __invert__(self): return self._unary("not_")
+    def __abs__(self): return self._unary("abs")
+
+    # ---- reductions (rstsr-core/src/tensor/reduction.rs:3-133) ----
+    def _reduce(self, op: str, axes=None):
+        dev = self.device
+        if axes is None:
+            return dev.reduce_all(op, self.raw, self.layout)
+        if isinstance(axes, int):
+            axes = [axes]
+        raw, lo = dev.reduce_axes(op, self.raw, self.layout, list(axes))
+        return Tensor(raw, lo)
+
+    def sum_all(self): return self._reduce("sum")
+    def prod_all(self): return self._reduce("prod")
+    def max_all(self): return self._reduce("max")
+    def min_all(self): return self._reduce("min")
+    def mean_all(self): return self._reduce("mean")
+    def sum_axes(self, axes): return self._reduce("sum", axes)
+    def prod_axes(self, axes): return self._reduce("prod", axes)
+    def max_axes(self, axes): return self._reduce("max", axes)
+    def min_axes(self, axes): return self._reduce("min", axes)
+    def mean_axes(self, axes): return self._reduce("mean", axes)
+    sum, prod, max, min, mean = sum_all, prod_all, max_all, min_all, mean_all
+
+
+# ---- creation (rstsr-core/src/tensor/{asarray,creation}.rs) ----
+def asarray(data, device: DeviceCuda, layout: Optional[Layout] = None, dtype=None) -> Tensor:
+    """asarray((vec, layout, &device)): upload a flat vector and view it through `layout`; a numpy array is
+    uploaded as is (its C-order flattening) with the device's default-order contiguous layout of its shape."""
+    arr = np.asarray(data, dtype=dtype)
+    shape = arr.shape
+    raw = device.outof_cpu_vec(arr.reshape(-1))
+    if layout is None:
+        if arr.ndim <= 1 or device.default_order() == ROW_MAJOR:
+            layout = Layout.contig(shape, ROW_MAJOR)
+        else:
+            # keep the values at the same logical indices: the upload is C-ordered
+            layout = Layout.contig(shape, ROW_MAJOR)
+    return Tensor(raw, layout)
+
+
+def arange(n: int, device: DeviceCuda, dtype=np.int64) -> Tensor:
+    return asarray(np.arange(n, dtype=dtype), device)
+
+
+def zeros(shape: Sequence[int], device: DeviceCuda, dtype=np.float64) -> Tensor:
+    l = Layout.contig(shape, device.default_order())
+    return Tensor(device.zeros_impl(dtype, max(l.size, 1)), l)
+
+
+def full(shape: Sequence[int], value, device: DeviceCuda, dtype=np.float64) -> Tensor:
+    l = Layout.contig(shape, device.default_order())
+    return Tensor(device.full_impl(dtype, max(l.size, 1), value), l)
+
+
+def empty(shape: Sequence[int], device: DeviceCuda, dtype=np.float64) -> Tensor:
+    l = Layout.contig(shape, device.default_order())
+    return Tensor(device.uninit_impl(dtype, max(l.size, 1)), l)
