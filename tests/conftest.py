@@ -1,0 +1,35 @@
+"""pytest configuration: the `gpu` marker and shared fixtures.
+
+`-m "not gpu"`: oracle vs the reference's known-answer vectors, the product's host-side layout algebra vs the
+oracle, C-ABI symbol/loader checks, the shard planner under gloo (world_size 2).  No compute calls on a GPU.
+`-m gpu`: parity tests proper -- every call goes through the C ABI of librstsr_cuda.so and is compared with the
+oracle on the same seeded inputs.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def dev():
+    import rstsr_b200 as rt
+    d = rt.DeviceCuda(0, rt.ROW_MAJOR)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="session")
+def dev_col():
+    import rstsr_b200 as rt
+    d = rt.DeviceCuda(0, rt.COL_MAJOR)
+    yield d
+    d.close()
