@@ -293,6 +293,11 @@ def run_product(args, rank, local_rank, world):
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
     e2e = run_e2e(args, dev, rt, np, torch, dist, comm, world)
+    if dist is not None:
+        if comm is not None:
+            comm.close()
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank != 0:
         return
@@ -339,67 +344,116 @@ def run_product(args, rank, local_rank, world):
 
 
 def run_e2e(args, dev, rt, np, torch, dist, comm, world):
-    """Same step through the reference-facing calls with HOST data: outof_cpu_vec-style H2D of every input,
-    the op, to_cpu_vec-style D2H of every result.  Pinned host buffers; timed with CUDA events on the stream."""
-    from rstsr_b200 import Layout, _ffi
-    lib = _ffi.lib()
+    """Same step through the C ABI with HOST data: every input is copied from pinned host memory, every result
+    is copied back, all inside the timed region.  Three handles of the same GPU (upload / compute / download
+    streams, ordered with rc_device_wait) pipeline the step in chunks along each config's outermost axis, so
+    PCIe uploads, kernels and PCIe downloads overlap (full-duplex link): the step costs ~max(H2D, D2H) instead
+    of their sum.  Timed with CUDA events on the stream `dev` is bound to; the pipeline is fenced against it."""
+    from rstsr_b200 import Layout
     steps = max(1, min(args.steps, 3))
+    up = rt.DeviceCuda(dev.ordinal, rt.ROW_MAJOR)
+    cp = rt.DeviceCuda(dev.ordinal, rt.ROW_MAJOR)
+    dn = rt.DeviceCuda(dev.ordinal, rt.ROW_MAJOR)
+    ccomm = None
+    if comm is not None:  # the collective runs on the compute handle's stream
+        uid = [rt.Comm.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ccomm = rt.Comm(cp, world, dist.get_rank(), uid[0])
     pin = dict(dtype=torch.float64, pin_memory=True)
+    n2 = SHP2[0] * SHP2[1] * SHP2[2]
     h_a1 = torch.rand(N1 * N1, **pin); h_b1 = torch.rand(N1, **pin); h_c1 = torch.empty(N1 * N1, **pin)
-    h_s2 = torch.rand(SHP2[0] * SHP2[1] * SHP2[2], **pin); h_d2 = torch.empty_like(h_s2).pin_memory()
+    h_s2 = torch.rand(n2, **pin); h_d2 = torch.empty(n2, **pin)
     h_m3 = torch.rand(N3 * N3, **pin); h_or = torch.empty(N3, **pin); h_oc = torch.empty(N3, **pin)
-    d_a1 = dev.uninit_impl(np.float64, N1 * N1); d_b1 = dev.uninit_impl(np.float64, N1)
-    d_c1 = dev.uninit_impl(np.float64, N1 * N1)
-    d_s2 = dev.uninit_impl(np.float64, h_s2.numel()); d_d2 = dev.uninit_impl(np.float64, h_s2.numel())
-    d_m3 = dev.uninit_impl(np.float64, N3 * N3); d_or = dev.uninit_impl(np.float64, N3); d_oc = dev.uninit_impl(np.float64, N3)
-    la1 = Layout((N1, N1), (N1, 1)); lb1 = Layout((N1, N1), (0, 1))
-    lsrc2 = Layout((SHP2[2], SHP2[0], SHP2[1]), (1, SHP2[1] * SHP2[2], SHP2[2]))
-    ldst2 = Layout.contig(lsrc2.shape, rt.ROW_MAJOR)
+    d_a1 = cp.uninit_impl(np.float64, N1 * N1); d_b1 = cp.uninit_impl(np.float64, N1)
+    d_c1 = cp.uninit_impl(np.float64, N1 * N1)
+    d_s2 = cp.uninit_impl(np.float64, n2); d_d2 = cp.uninit_impl(np.float64, n2)
+    d_m3 = cp.uninit_impl(np.float64, N3 * N3); d_or = cp.uninit_impl(np.float64, N3); d_oc = cp.uninit_impl(np.float64, N3)
+    cp.synchronize()
     lm3 = Layout((N3, N3), (N3, 1)); lo3 = Layout((N3,), (1,))
-    h = dev._handle
-
-    def h2d(d, t):
-        _ffi.check(lib.rc_memcpy_h2d(h, d.ptr, t.data_ptr(), t.numel() * 8))
-
-    def d2h_async(t, d):
-        # rc_memcpy_d2h synchronises (to_cpu_vec semantics); the last read of the step does that for all of them
-        torch.cuda.current_stream()
-        _ffi.check(lib.rc_memcpy_d2h(h, t.data_ptr(), d.ptr, t.numel() * 8))
+    CH1, CH2, CH3 = 4, 16, 4
 
     def step():
-        h2d(d_a1, h_a1); h2d(d_b1, h_b1)
-        dev.op_mutc_refa_refb("add", d_c1, la1, d_a1, la1, d_b1, lb1)
-        d2h_async(h_c1, d_c1)
-        h2d(d_s2, h_s2)
-        dev.assign_arbitary(d_d2, ldst2, d_s2, lsrc2)
-        d2h_async(h_d2, d_d2)
-        h2d(d_m3, h_m3)
-        dev.reduce_axes_into("sum", d_m3, lm3, [-1], d_or, lo3)
-        dev.reduce_axes_into("sum", d_m3, lm3, [0], d_oc, lo3)
-        if comm is not None:
-            comm.all_reduce("sum", d_oc, N3)
-        d2h_async(h_or, d_or); d2h_async(h_oc, d_oc)
+        up.wait(cp); cp.wait(dn)  # do not overwrite inputs / outputs the previous step still uses
+        # cfg1: row chunks of c = a + b
+        up.h2d_async(d_b1, h_b1.data_ptr(), N1 * 8)
+        r = N1 // CH1
+        for k in range(CH1):
+            off = k * r * N1
+            up.h2d_async(d_a1, h_a1.data_ptr() + off * 8, r * N1 * 8, off * 8)
+            cp.wait(up)
+            cp.op_mutc_refa_refb("add", d_c1, Layout((r, N1), (N1, 1), off), d_a1, Layout((r, N1), (N1, 1), off),
+                                 d_b1, Layout((r, N1), (0, 1)))
+            dn.wait(cp)
+            dn.d2h_async(h_c1.data_ptr() + off * 8, d_c1, r * N1 * 8, off * 8)
+        # cfg2: chunks along the source's outermost axis i; each produces the slab dst[:, i0:i1, :]
+        ci = SHP2[0] // CH2
+        slab = SHP2[1] * SHP2[2]
+        for k in range(CH2):
+            i0 = k * ci
+            up.h2d_async(d_s2, h_s2.data_ptr() + i0 * slab * 8, ci * slab * 8, i0 * slab * 8)
+            cp.wait(up)
+            lsrc = Layout((SHP2[2], ci, SHP2[1]), (1, slab, SHP2[2]), i0 * slab)
+            ldst = Layout((SHP2[2], ci, SHP2[1]), (SHP2[0] * SHP2[1], SHP2[1], 1), i0 * SHP2[1])
+            cp.assign_arbitary(d_d2, ldst, d_s2, lsrc)
+            dn.wait(cp)
+            pitch = SHP2[0] * SHP2[1] * 8
+            dn.d2h_2d_async(h_d2.data_ptr() + i0 * SHP2[1] * 8, pitch, d_d2, i0 * SHP2[1] * 8, pitch,
+                            ci * SHP2[1] * 8, SHP2[2])
+        # cfg3: upload in row blocks, reduce once the matrix is resident
+        r = N3 // CH3
+        for k in range(CH3):
+            up.h2d_async(d_m3, h_m3.data_ptr() + k * r * N3 * 8, r * N3 * 8, k * r * N3 * 8)
+        cp.wait(up)
+        cp.reduce_axes_into("sum", d_m3, lm3, [-1], d_or, lo3)
+        cp.reduce_axes_into("sum", d_m3, lm3, [0], d_oc, lo3)
+        if ccomm is not None:
+            ccomm.all_reduce("sum", d_oc, N3)
+        dn.wait(cp)
+        dn.d2h_async(h_or.data_ptr(), d_or, N3 * 8)
+        dn.d2h_async(h_oc.data_ptr(), d_oc, N3 * 8)
 
-    step()
+    def fence_start():
+        for h in (up, cp, dn):
+            h.wait(dev)
+
+    def fence_end():
+        for h in (up, cp, dn):
+            dev.wait(h)
+
+    fence_start(); step(); fence_end()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
+    fence_start()
     for _ in range(steps):
         step()
+    fence_end()
     e1.record()
     torch.cuda.synchronize()
     sec = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(sec, op=dist.ReduceOp.MAX)
     sec = float(sec.item())
+    # the host results are the real thing
     assert torch.equal(h_c1.view(N1, N1), h_a1.view(N1, N1) + h_b1)
+    want = h_s2.view(*SHP2)[700:702].permute(2, 0, 1).contiguous()
+    assert torch.equal(h_d2.view(SHP2[2], SHP2[0], SHP2[1])[:, 700:702, :], want)
+    ref_r = h_m3.view(N3, N3).sum(dim=1)
+    assert float(((h_or - ref_r).abs() / ref_r.abs()).max()) < 1e-12
+    if ccomm is None:
+        ref_c = h_m3.view(N3, N3).sum(dim=0)
+        assert float(((h_oc - ref_c).abs() / ref_c.abs()).max()) < 1e-12
     h2d_bytes = (h_a1.numel() + h_b1.numel() + h_s2.numel() + h_m3.numel()) * 8
     d2h_bytes = (h_c1.numel() + h_d2.numel() + h_or.numel() + h_oc.numel()) * 8
+    if ccomm is not None:
+        ccomm.close()
     return {"value": round(world * BYTES_STEP * steps / sec / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
             "d2h_bytes_per_step": d2h_bytes, "steps": steps, "ms_per_step": round(sec / steps * 1e3, 2),
-            "path": "rc_memcpy_h2d -> rc_op_mutc_refa_refb / rc_assign_arbitary / rc_reduce_axes_into -> rc_memcpy_d2h"}
+            "path": "pinned host -> rc_memcpy_h2d_async -> rc_op_mutc_refa_refb / rc_assign_arbitary / "
+                    "rc_reduce_axes_into -> rc_memcpy(2d)_d2h_async -> pinned host; upload/compute/download handles "
+                    "ordered by rc_device_wait, chunked 4/16/4"}
 
 
 def main():

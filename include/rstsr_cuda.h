@@ -192,6 +192,19 @@ int rc_memcpy_h2d(rc_device *dev, void *dst_dev, const void *src_host, size_t nb
 int rc_memcpy_d2h(rc_device *dev, void *dst_host, const void *src_dev, size_t nbytes); /* synchronises */
 int rc_memcpy_d2d(rc_device *dev, void *dst_dev, const void *src_dev, size_t nbytes);
 int rc_memset(rc_device *dev, void *dst_dev, int byte, size_t nbytes);
+/* Stream-ordered transfers for pipelined staging (outof_cpu_vec / to_cpu_vec of large tensors): nothing
+ * synchronises; the host buffer must be pinned (rc_host_alloc) and stay alive until rc_device_synchronize.
+ * The 2-D form moves `height` rows of `width_bytes` with independent pitches (a strided slab of a tensor). */
+int rc_memcpy_h2d_async(rc_device *dev, void *dst_dev, const void *src_host, size_t nbytes);
+int rc_memcpy_d2h_async(rc_device *dev, void *dst_host, const void *src_dev, size_t nbytes);
+int rc_memcpy2d_d2h_async(rc_device *dev, void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch,
+                          size_t width_bytes, size_t height);
+int rc_memcpy2d_h2d_async(rc_device *dev, void *dst_dev, size_t dst_pitch, const void *src_host, size_t src_pitch,
+                          size_t width_bytes, size_t height);
+/* Cross-handle ordering: everything enqueued on `waiter` after this call runs after everything enqueued on
+ * `signaler` before it (cudaEventRecord + cudaStreamWaitEvent).  Handles of one ordinal are "the same device"
+ * (rc_device_same_device); using several of them is how copies overlap kernels. */
+int rc_device_wait(rc_device *waiter, rc_device *signaler);
 int rc_get_index(rc_device *dev, rc_dtype dtype, const void *a, int64_t index, void *host_out);
 int rc_set_index(rc_device *dev, rc_dtype dtype, void *a, int64_t index, const void *host_value);
 /* pinned host staging buffers for outof_cpu_vec / to_cpu_vec */

@@ -270,6 +270,49 @@ int rc_memcpy_d2d(rc_device *dev, void *dst, const void *src, size_t nbytes) {
         RC_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, dev->stream));
     });
 }
+int rc_memcpy_h2d_async(rc_device *dev, void *dst, const void *src, size_t nbytes) {
+    return rc_memcpy_h2d(dev, dst, src, nbytes);  // already stream-ordered and non-blocking for pinned memory
+}
+int rc_memcpy_d2h_async(rc_device *dev, void *dst, const void *src, size_t nbytes) {
+    return guard([&] {
+        DeviceGuard g(dev);
+        if (nbytes == 0) return;
+        check_ptr(dst, "dst"); check_ptr(src, "src");
+        RC_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, dev->stream));
+    });
+}
+int rc_memcpy2d_d2h_async(rc_device *dev, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                          size_t height) {
+    return guard([&] {
+        DeviceGuard g(dev);
+        if (width == 0 || height == 0) return;
+        check_ptr(dst, "dst"); check_ptr(src, "src");
+        RC_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, dev->stream));
+    });
+}
+int rc_memcpy2d_h2d_async(rc_device *dev, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                          size_t height) {
+    return guard([&] {
+        DeviceGuard g(dev);
+        if (width == 0 || height == 0) return;
+        check_ptr(dst, "dst"); check_ptr(src, "src");
+        RC_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, dev->stream));
+    });
+}
+int rc_device_wait(rc_device *waiter, rc_device *signaler) {
+    return guard([&] {
+        RC_CHECK(waiter && signaler, RC_ERR_INVALID_VALUE, "null device handle");
+        RC_CHECK(waiter->ordinal == signaler->ordinal, RC_ERR_DEVICE_MISMATCH, "handles belong to different GPUs");
+        DeviceGuard g(waiter);
+        if (waiter->stream == signaler->stream) return;
+        cudaEvent_t ev;
+        RC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, signaler->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(waiter->stream, ev, 0);
+        cudaEventDestroy(ev);  // released once the wait has been satisfied
+        if (e != cudaSuccess) raise(RC_ERR_DEVICE, std::string("rc_device_wait: ") + cudaGetErrorString(e));
+    });
+}
 int rc_memset(rc_device *dev, void *dst, int byte, size_t nbytes) {
     return guard([&] {
         DeviceGuard g(dev);

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
     using TA = typename F::TA;
     using TB = typename F::TB;
     using TO = typename F::TO;
+    static_assert(TILE_X == TILE_Y, "slot mapping below assumes a square tile");
     constexpr int PITCH = TILE_Y + 1;  // odd pitch: column reads hit distinct banks (8-byte: per half-warp)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TA *sa = reinterpret_cast<TA *>(smem_raw);
@@ -271,78 +272,74 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
         t = q;
     }
     const uint32_t x0 = tx * TILE_X, y0 = ty * TILE_Y;
+    const uint32_t remx = d.nx - x0, remy = d.ny - y0;  // valid extent of this tile
 
-    // phase 1: staged operands, lanes along Y (their contiguous axis)
-    constexpr int RX = TILE_X / TILE_WARPS, CY = TILE_Y / 32;
-    if (mode_a == TILE_STAGED) {
-        TA reg[RX][CY];
+    // Slot (r, j) of a thread has tile coordinates (u, v) = (warp + 8 r, lane + 32 j).  A STAGED operand is read
+    // with (x, y) = (u, v): lanes run along Y, its contiguous axis.  A DIRECT operand and the output use
+    // (y, x) = (u, v): lanes run along X.  One register array per operand serves either role, every load is a
+    // predicated in-place LDG, and all loads of both operands are issued before anything is consumed.
+    constexpr int R = TILE_X / TILE_WARPS, C = TILE_Y / 32;
+    const bool stg_a = (F::NIN >= 1) && mode_a == TILE_STAGED, dir_a = (F::NIN >= 1) && mode_a == TILE_DIRECT;
+    const bool stg_b = (F::NIN >= 2) && mode_b == TILE_STAGED, dir_b = (F::NIN >= 2) && mode_b == TILE_DIRECT;
+    // element offset of slot (u, v): (p0 + u) * su + (q0 + v) * sv
+    const int64_t su_a = stg_a ? d.sx[1] : d.sy[1], sv_a = stg_a ? d.sy[1] : d.sx[1];
+    const int64_t su_b = stg_b ? d.sx[2] : d.sy[2], sv_b = stg_b ? d.sy[2] : d.sx[2];
+    const TA *pa = a + base[1] + (int64_t)(stg_a ? x0 : y0) * su_a + (int64_t)(stg_a ? y0 : x0) * sv_a;
+    const TB *pb = b + base[2] + (int64_t)(stg_b ? x0 : y0) * su_b + (int64_t)(stg_b ? y0 : x0) * sv_b;
+    const uint32_t lim_u_a = stg_a ? remx : remy, lim_v_a = stg_a ? remy : remx;
+    const uint32_t lim_u_b = stg_b ? remx : remy, lim_v_b = stg_b ? remy : remx;
+
+    Pack<TA, 1> ra[R][C];
+    Pack<TB, 1> rb[R][C];
 #pragma unroll
-        for (int r = 0; r < RX; ++r) {
-            uint32_t x = x0 + warp + r * TILE_WARPS;
+    for (int r = 0; r < R; ++r) {
+        const uint32_t u = warp + r * TILE_WARPS;
 #pragma unroll
-            for (int j = 0; j < CY; ++j) {
-                uint32_t y = y0 + lane + 32 * j;
-                if (x < d.nx && y < d.ny) reg[r][j] = __ldcs(a + base[1] + (int64_t)x * d.sx[1] + y);
+        for (int j = 0; j < C; ++j) {
+            const uint32_t v = lane + 32 * j;
+            ra[r][j].v[0] = ka.v;
+            if constexpr (F::NIN >= 1)
+                ld_stream_pred<TA, 1>(ra[r][j], pa + (int64_t)u * su_a + (int64_t)v * sv_a,
+                                      (stg_a || dir_a) && u < lim_u_a && v < lim_v_a);
+            if constexpr (F::NIN >= 2) {
+                rb[r][j].v[0] = kb.v;
+                ld_stream_pred<TB, 1>(rb[r][j], pb + (int64_t)u * su_b + (int64_t)v * sv_b,
+                                      (stg_b || dir_b) && u < lim_u_b && v < lim_v_b);
             }
         }
-#pragma unroll
-        for (int r = 0; r < RX; ++r)
-#pragma unroll
-            for (int j = 0; j < CY; ++j) sa[(warp + r * TILE_WARPS) * PITCH + lane + 32 * j] = reg[r][j];
     }
-    if (F::NIN > 1 && mode_b == TILE_STAGED) {
-        TB reg[RX][CY];
+    if (stg_a) {
 #pragma unroll
-        for (int r = 0; r < RX; ++r) {
-            uint32_t x = x0 + warp + r * TILE_WARPS;
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < CY; ++j) {
-                uint32_t y = y0 + lane + 32 * j;
-                if (x < d.nx && y < d.ny) reg[r][j] = __ldcs(b + base[2] + (int64_t)x * d.sx[2] + y);
-            }
-        }
+            for (int j = 0; j < C; ++j) sa[(warp + r * TILE_WARPS) * PITCH + lane + 32 * j] = ra[r][j].v[0];
+    }
+    if (stg_b) {
 #pragma unroll
-        for (int r = 0; r < RX; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < CY; ++j) sb[(warp + r * TILE_WARPS) * PITCH + lane + 32 * j] = reg[r][j];
+            for (int j = 0; j < C; ++j) sb[(warp + r * TILE_WARPS) * PITCH + lane + 32 * j] = rb[r][j].v[0];
     }
     __syncthreads();
 
-    // phase 2: lanes along X (the output's contiguous axis)
-    constexpr int RY = TILE_Y / TILE_WARPS, CX = TILE_X / 32;
-    TA xa[RY][CX];
-    TB xb[RY][CX];
+    // phase 2: slot (u, v) = (y, x); lanes along X, the output's contiguous axis
+    TO *pc = c + base[0] + (int64_t)y0 * d.sy[0] + x0;
 #pragma unroll
-    for (int r = 0; r < RY; ++r) {
-        uint32_t y = y0 + warp + r * TILE_WARPS;
+    for (int r = 0; r < R; ++r) {
+        const uint32_t u = warp + r * TILE_WARPS;
 #pragma unroll
-        for (int j = 0; j < CX; ++j) {
-            uint32_t x = x0 + lane + 32 * j;
-            if (x < d.nx && y < d.ny) {
-                if (mode_a == TILE_DIRECT) xa[r][j] = __ldcs(a + base[1] + (int64_t)x * d.sx[1] + (int64_t)y * d.sy[1]);
-                if (F::NIN > 1 && mode_b == TILE_DIRECT)
-                    xb[r][j] = __ldcs(b + base[2] + (int64_t)x * d.sx[2] + (int64_t)y * d.sy[2]);
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RY; ++r) {
-        const int yl = warp + r * TILE_WARPS;
-        uint32_t y = y0 + yl;
-#pragma unroll
-        for (int j = 0; j < CX; ++j) {
-            const int xl = lane + 32 * j;
-            uint32_t x = x0 + xl;
-            if (x < d.nx && y < d.ny) {
-                TA va = (mode_a == TILE_DIRECT) ? xa[r][j] : (mode_a == TILE_STAGED ? sa[xl * PITCH + yl] : ka.v);
+        for (int j = 0; j < C; ++j) {
+            const uint32_t v = lane + 32 * j;
+            if (u < remy && v < remx) {
+                const TA va = stg_a ? sa[v * PITCH + u] : ra[r][j].v[0];
                 TO out;
                 if constexpr (F::NIN > 1) {
-                    TB vb = (mode_b == TILE_DIRECT) ? xb[r][j] : (mode_b == TILE_STAGED ? sb[xl * PITCH + yl] : kb.v);
+                    const TB vb = stg_b ? sb[v * PITCH + u] : rb[r][j].v[0];
                     out = F::apply(va, vb);
                 } else {
                     out = F::apply(va);
                 }
-                __stcs(c + base[0] + (int64_t)y * d.sy[0] + x, out);
+                __stcs(pc + (int64_t)u * d.sy[0] + v, out);
             }
         }
     }

@@ -263,6 +263,22 @@ class DeviceCuda:
         check(_ffi.lib().rc_memcpy_d2h(self._handle, out.ctypes.data, raw.ptr, raw.nbytes))
         return out
 
+    # ---- stream-ordered staging (pinned host memory); see rc_memcpy_*_async in the header ----
+    def wait(self, other: "DeviceCuda"):
+        """Work enqueued on this handle from now on runs after what `other` has enqueued so far."""
+        check(_ffi.lib().rc_device_wait(self._handle, other._handle))
+
+    def h2d_async(self, raw: CudaRaw, host_ptr: int, nbytes: int, dst_byte_offset: int = 0):
+        check(_ffi.lib().rc_memcpy_h2d_async(self._handle, raw.ptr + dst_byte_offset, host_ptr, nbytes))
+
+    def d2h_async(self, host_ptr: int, raw: CudaRaw, nbytes: int, src_byte_offset: int = 0):
+        check(_ffi.lib().rc_memcpy_d2h_async(self._handle, host_ptr, raw.ptr + src_byte_offset, nbytes))
+
+    def d2h_2d_async(self, host_ptr: int, host_pitch: int, raw: CudaRaw, src_byte_offset: int, src_pitch: int,
+                     width_bytes: int, height: int):
+        check(_ffi.lib().rc_memcpy2d_d2h_async(self._handle, host_ptr, host_pitch, raw.ptr + src_byte_offset, src_pitch,
+                                               width_bytes, height))
+
     def wrap(self, ptr: int, length: int, dtype) -> CudaRaw:
         """Borrow device memory owned by someone else (e.g. a torch tensor's data_ptr())."""
         return CudaRaw(self, ptr, length, dtype, owned=False)
