@@ -151,7 +151,18 @@ typedef enum rc_unop {
 } rc_unop;
 
 /* reductions: Op{Sum,Min,Max,Prod,Mean}API (rstsr-core/src/operators/reduction.rs:3-33) */
-typedef enum rc_redop { RC_SUM = 0, RC_PROD = 1, RC_MAX = 2, RC_MIN = 3, RC_MEAN = 4 } rc_redop;
+typedef enum rc_redop {
+    RC_SUM = 0, RC_PROD = 1, RC_MAX = 2, RC_MIN = 3, RC_MEAN = 4,
+    /* "next" reductions (same kernels, other monoids; operators/reduction.rs:35-95): */
+    RC_VAR = 5,            /* population variance q/n - (s/n)^2 (auto_impl/reduction.rs:207-262) */
+    RC_STD = 6,
+    RC_L2_NORM = 7,
+    RC_ARGMIN = 8,         /* output u64: row-major index within the reduced axes (in the order given) */
+    RC_ARGMAX = 9,
+    RC_ALL = 10,           /* bool -> bool */
+    RC_ANY = 11,
+    RC_COUNT_NONZERO = 12  /* any dtype -> u64; on bool this is OpSumBoolAPI */
+} rc_redop;
 
 typedef struct rc_device rc_device; /* opaque: {ordinal, default_order, stream, workspaces} */
 
@@ -276,6 +287,8 @@ int rc_op_muta_numb(rc_device *dev, rc_binop op, rc_dtype dtype, void *a, const 
 int rc_unary_muta_refb(rc_device *dev, rc_unop op, rc_dtype dtype, void *a, const rc_layout *la, const void *b,
                        const rc_layout *lb);
 int rc_unary_muta(rc_device *dev, rc_unop op, rc_dtype dtype, void *a, const rc_layout *la);
+/* output dtype of a reduction (u64 for arg* and count_nonzero, bool for all/any, else the element type) */
+int rc_redop_out_dtype(rc_redop op, rc_dtype dtype, rc_dtype *out);
 /* output dtype of an elementwise op for operand dtype `dtype` (bool for comparisons/predicates) */
 int rc_binop_out_dtype(rc_binop op, rc_dtype dtype, rc_dtype *out);
 int rc_unop_out_dtype(rc_unop op, rc_dtype dtype, rc_dtype *out);

@@ -339,3 +339,79 @@ def to_numpy(raw: np.ndarray, l: Layout) -> np.ndarray:
     view = np.lib.stride_tricks.as_strided(raw[l.offset:] if l.offset <= raw.size else raw, shape=l.shape,
                                            strides=tuple(s * item for s in l.stride), writeable=False)
     return np.array(view)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" reductions: var / std / l2_norm / argmin / argmax / all / any / count_nonzero.
+# Closures of rstsr-core/src/feature_rayon/auto_impl/reduction.rs:207-715; arg semantics of
+# rstsr-native-impl/src/cpu_serial/reduction.rs:421-582 (row-major first occurrence, NaN never accepted unless it
+# is the first element).  Evaluated with numpy / plain Python on the materialised view: values, not loop order,
+# are what these pin (float results are compared with a tolerance anyway).
+# ---------------------------------------------------------------------------------------------
+def _arg_fold(values, is_max: bool) -> int:
+    """reduce_all_unraveled_arg_cpu_serial's fold over a row-major sequence -> row-major index."""
+    acc_i, acc_v = None, None
+    for i, y in enumerate(values):
+        if acc_i is None:
+            acc_i, acc_v = i, y  # f_comp(None, y) = Some(true)
+            continue
+        better = (y > acc_v) if is_max else (y < acc_v)
+        if better:
+            acc_i, acc_v = i, y
+        # equal values: the smaller index stays (iteration is in increasing index order)
+    return acc_i
+
+
+def reduce_ext(op: str, a, la: Layout, axes=None):
+    """-> (raw output, output layout) for axes, or a scalar for axes=None."""
+    if op in ("argmin", "argmax") and la.size == 0:
+        raise LayoutError("InvalidLayout", "empty sequence is not allowed for reduce_arg.")
+    view = to_numpy(a, la)
+    nd = la.ndim
+    if axes is None:
+        ax = list(range(nd))
+    else:
+        ax = L.normalize_axes(axes, nd)
+    kept = [i for i in range(nd) if i not in ax]
+    # reduced axes in the ORDER GIVEN, flattened row-major (layout_axes of dim_split_axes keeps that order)
+    moved = np.transpose(view, kept + ax)
+    kshape = tuple(la.shape[i] for i in kept)
+    n_red = 1
+    for i in ax:
+        n_red *= la.shape[i]
+    flat = moved.reshape(kshape + (n_red,))
+    dt = a.dtype
+    if op in ("var", "std"):
+        s = flat.sum(-1, dtype=dt)
+        q = (flat * flat).sum(-1, dtype=dt)
+        n = dt.type(n_red)
+        mean = s / n
+        res = q / n - mean * mean
+        if op == "std":
+            res = np.sqrt(res)
+        res = res.astype(dt)
+    elif op == "l2_norm":
+        res = np.sqrt((flat * flat).sum(-1, dtype=dt)).astype(dt)
+    elif op in ("argmin", "argmax"):
+        res = np.zeros(kshape, dtype=np.uint64)
+        it = np.ndindex(*kshape) if kshape else [()]
+        for idx in it:
+            res[idx] = _arg_fold(list(flat[idx]), op == "argmax")
+    elif op == "count_nonzero":
+        res = (flat != 0).sum(-1).astype(np.uint64)
+    elif op == "all":
+        res = flat.astype(bool).all(-1)
+    elif op == "any":
+        res = flat.astype(bool).any(-1)
+    else:
+        raise ValueError(op)
+    if axes is None:
+        return res.reshape(())[()]
+    _, lm = L.dim_split_axes(la, ax)
+    lo = L.layout_for_array_copy(lm, "K")
+    out = np.zeros(max(lo.size, 1), dtype=res.dtype)
+    if lo.size:
+        item = out.dtype.itemsize
+        dst = np.lib.stride_tricks.as_strided(out, shape=lo.shape, strides=tuple(s * item for s in lo.stride))
+        dst[...] = res
+    return out, lo

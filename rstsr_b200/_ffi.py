@@ -30,7 +30,8 @@ UNOPS = dict(neg=0, not_=1, abs=2, square=3, sign=4, sqrt=5, exp=6, expm1=7, log
              tan=13, asin=14, acos=15, atan=16, sinh=17, cosh=18, tanh=19, asinh=20, acosh=21, atanh=22, floor=23,
              ceil=24, round=25, trunc=26, reciprocal=27, conj=28, real=29, imag=30, isnan=48, isinf=49, isfinite=50,
              signbit=51)
-REDOPS = dict(sum=0, prod=1, max=2, min=3, mean=4)
+REDOPS = dict(sum=0, prod=1, max=2, min=3, mean=4, var=5, std=6, l2_norm=7, argmin=8, argmax=9, all=10, any=11,
+              count_nonzero=12)
 
 
 class RstsrCudaError(RuntimeError):
@@ -104,6 +105,7 @@ SIGNATURES = {
     "rc_unary_muta": (c_int, [_P, c_int, c_int, _P, _L]),
     "rc_binop_out_dtype": (c_int, [c_int, c_int, POINTER(c_int)]),
     "rc_unop_out_dtype": (c_int, [c_int, c_int, POINTER(c_int)]),
+    "rc_redop_out_dtype": (c_int, [c_int, c_int, POINTER(c_int)]),
     "rc_reduce_all": (c_int, [_P, c_int, c_int, _P, _L, _P]),
     "rc_reduce_all_device": (c_int, [_P, c_int, c_int, _P, _L, _P]),
     "rc_reduce_axes": (c_int, [_P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, POINTER(_P), _L]),

@@ -34,9 +34,37 @@ void run_reduce_i64(rc_device *, rc_redop, const CanonRed &, const void *, void 
 void run_reduce_u64(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 void run_reduce_i32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 void run_reduce_u32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_ext_f64(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_ext_f32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_ext_i64(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_ext_u64(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_ext_i32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_ext_u32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_bool(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+
+rc_dtype redop_out_dtype(rc_redop op, rc_dtype t) {
+    switch (op) {
+        case RC_ARGMIN: case RC_ARGMAX: case RC_COUNT_NONZERO: return RC_U64;
+        case RC_ALL: case RC_ANY: return RC_BOOL;
+        default: return t;
+    }
+}
 
 void run_reduce(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out,
                 int64_t mean_count) {
+    if (op >= RC_VAR) {  // the "next" reductions
+        switch (t) {
+            case RC_F64: run_reduce_ext_f64(dev, op, cr, a, out, mean_count); return;
+            case RC_F32: run_reduce_ext_f32(dev, op, cr, a, out, mean_count); return;
+            case RC_I64: run_reduce_ext_i64(dev, op, cr, a, out, mean_count); return;
+            case RC_U64: run_reduce_ext_u64(dev, op, cr, a, out, mean_count); return;
+            case RC_I32: run_reduce_ext_i32(dev, op, cr, a, out, mean_count); return;
+            case RC_U32: run_reduce_ext_u32(dev, op, cr, a, out, mean_count); return;
+            case RC_BOOL: run_reduce_bool(dev, op, cr, a, out, mean_count); return;
+            default: break;
+        }
+        raise(RC_ERR_UNIMPLEMENTED, std::string("reduction is not implemented for dtype ") + dtype_name(t));
+    }
     switch (t) {
         case RC_F64: run_reduce_f64(dev, op, cr, a, out, mean_count); return;
         case RC_F32: run_reduce_f32(dev, op, cr, a, out, mean_count); return;
@@ -123,10 +151,15 @@ void reduce_into(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const L
     if (op == RC_MAX || op == RC_MIN)
         RC_CHECK(la.size() != 0, RC_ERR_INVALID_VALUE,
                  op == RC_MAX ? "zero-size array is not supported for max" : "zero-size array is not supported for min");
-    if (op == RC_MEAN) RC_CHECK(dtype_is_float(t), RC_ERR_UNIMPLEMENTED, "mean requires a floating-point dtype");
+    if (op == RC_MEAN || op == RC_VAR || op == RC_STD || op == RC_L2_NORM)
+        RC_CHECK(dtype_is_float(t), RC_ERR_UNIMPLEMENTED, "mean / var / std / l2_norm require a floating-point dtype");
+    if (op == RC_ALL || op == RC_ANY) RC_CHECK(t == RC_BOOL, RC_ERR_UNIMPLEMENTED, "all / any take a bool tensor");
+    const bool arg = (op == RC_ARGMIN || op == RC_ARGMAX);
+    if (arg)  // reduce_all_unraveled_arg_cpu_serial: "empty sequence is not allowed for reduce_arg."
+        RC_CHECK(la.size() != 0, RC_ERR_INVALID_LAYOUT, "empty sequence is not allowed for reduce_arg.");
     Layout l_axes;
     split_axes(la, axes, &l_axes, nullptr, nullptr);  // validates both halves like the reference
-    CanonRed cr = canon_reduce(la, axes, lo);
+    CanonRed cr = canon_reduce(la, axes, lo, /*keep_order=*/arg);
     std::lock_guard<std::mutex> lock(dev->ws_mu);
     run_reduce(dev, op, t, cr, a, out, l_axes.size());
 }
@@ -601,6 +634,9 @@ int rc_binop_out_dtype(rc_binop op, rc_dtype t, rc_dtype *out) {
 int rc_unop_out_dtype(rc_unop op, rc_dtype t, rc_dtype *out) {
     return guard([&] { RC_CHECK(out, RC_ERR_INVALID_VALUE, "null out"); *out = is_predicate(op) ? RC_BOOL : t; });
 }
+int rc_redop_out_dtype(rc_redop op, rc_dtype t, rc_dtype *out) {
+    return guard([&] { RC_CHECK(out, RC_ERR_INVALID_VALUE, "null out"); *out = redop_out_dtype(op, t); });
+}
 
 /* ---------------- reductions ---------------- */
 int rc_reduce_all_device(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const rc_layout *la_, void *dev_out) {
@@ -626,7 +662,7 @@ int rc_reduce_all(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const 
         try {
             Layout lo;
             reduce_into(dev, op, t, a, la, all_axes(la.ndim()), slot, lo);
-            RC_CUDA(cudaMemcpyAsync(host_out, slot, dtype_size(t), cudaMemcpyDeviceToHost, dev->stream));
+            RC_CUDA(cudaMemcpyAsync(host_out, slot, dtype_size(redop_out_dtype(op, t)), cudaMemcpyDeviceToHost, dev->stream));
             RC_CUDA(cudaStreamSynchronize(dev->stream));
         } catch (...) {
             cudaFreeAsync(slot, dev->stream);
@@ -658,7 +694,7 @@ int rc_reduce_axes(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const
             RC_CHECK(la.size() != 0, RC_ERR_INVALID_VALUE,
                      op == RC_MAX ? "zero-size array is not supported for max" : "zero-size array is not supported for min");
         Layout lo = layout_for_reduce(la, ax);
-        size_t nbytes = (size_t)std::max<int64_t>(lo.size(), 1) * dtype_size(t);
+        size_t nbytes = (size_t)std::max<int64_t>(lo.size(), 1) * dtype_size(redop_out_dtype(op, t));
         void *p = nullptr;
         cudaError_t e = cudaMallocAsync(&p, nbytes, dev->stream);
         if (e != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));

@@ -122,7 +122,7 @@ bool refine_to_common_shape(const Layout &lc_in, const Layout &la_in, rc_order o
     return true;
 }
 
-CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layout &lo) {
+CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layout &lo, bool keep_order) {
     CanonRed c;
     c.base_in = la.offset;
     c.base_out = lo.offset;
@@ -160,16 +160,18 @@ CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layo
     }
     struct R { int64_t n, s; };
     std::vector<R> rs;
-    for (int i : axes) {
+    for (size_t k = 0; k < axes.size(); ++k) {
+        // keep_order: fastest reduced dim = LAST axis given (row-major flattening of the reduced space)
+        int i = keep_order ? axes[axes.size() - 1 - k] : axes[k];
         if (la.shape[i] == 1) continue;
         R r{la.shape[i], la.stride[i]};
-        if (r.s < 0 && r.n > 0) {  // a reduction may walk any axis in either direction
+        if (!keep_order && r.s < 0 && r.n > 0) {  // an order-free reduction may walk any axis in either direction
             c.base_in += (r.n - 1) * r.s;
             r.s = -r.s;
         }
         rs.push_back(r);
     }
-    std::stable_sort(rs.begin(), rs.end(), [](const R &a, const R &b) { return a.s < b.s; });
+    if (!keep_order) std::stable_sort(rs.begin(), rs.end(), [](const R &a, const R &b) { return a.s < b.s; });
     for (const R &r : rs) {
         if (!c.rshape.empty()) {
             size_t p = c.rshape.size() - 1;

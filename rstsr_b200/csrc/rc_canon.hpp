@@ -43,6 +43,8 @@ struct CanonRed {
     int64_t n_out() const { int64_t s = 1; for (auto d : kshape) s *= d; return s; }
     int64_t n_red() const { int64_t s = 1; for (auto d : rshape) s *= d; return s; }
 };
-CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layout &lo);
+// keep_order: the reduced dims keep the row-major order of `axes` (dim 0 = last axis given), are never flipped
+// or sorted and only merged when adjacent -- the flat reduced index then IS the row-major index arg* ops return.
+CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layout &lo, bool keep_order = false);
 
 }  // namespace rc

@@ -140,6 +140,7 @@ int rc_reduce_all_sharded(rc_device *dev, rc_comm *comm, rc_redop op, rc_dtype t
         DeviceGuard g(dev);
         RC_CHECK(comm != nullptr && comm->dev == dev, RC_ERR_DEVICE_MISMATCH, "communicator belongs to another device");
         RC_CHECK(host_out != nullptr, RC_ERR_INVALID_VALUE, "null host_out");
+        RC_CHECK(op <= RC_MEAN, RC_ERR_UNIMPLEMENTED, "sharded reductions cover sum / prod / max / min / mean");
         void *slot = nullptr;
         cudaError_t e = cudaMallocAsync(&slot, 16, dev->stream);
         if (e != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));

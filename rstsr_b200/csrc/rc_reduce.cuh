@@ -1,20 +1,24 @@
-// rc_reduce.cuh -- kernel families K3/K4: sum / prod / max / min / mean over all or selected axes.
+// rc_reduce.cuh -- kernel families K3/K4: reductions over all or selected axes.
 //
-// Replaces rstsr-native-impl/src/cpu_rayon/reduction.rs:20-328 (reduce_all_cpu_rayon, reduce_axes_cpu_rayon)
-// with the (init, f, f_sum, f_out) monoids of rstsr-core/src/feature_rayon/auto_impl/reduction.rs:7-205:
-//   sum: 0, +      prod: 1, *      max: T::MIN, ext_max      min: T::MAX, ext_min      mean: sum, then / n
+// Replaces rstsr-native-impl/src/cpu_rayon/reduction.rs:20-328 (reduce_all_cpu_rayon, reduce_axes_cpu_rayon) and
+// the arg variants (cpu_serial/reduction.rs:421-582) with the (init, f, f_sum, f_out) monoids of
+// rstsr-core/src/feature_rayon/auto_impl/reduction.rs:
+//   sum: 0, +      prod: 1, *      max: T::MIN, ext_max      min: T::MAX, ext_min      mean: sum, then / n   (:7-205)
+//   var/std: (sum x, sum x^2) -> q/n - (s/n)^2 [, sqrt]      l2_norm: sum x^2 -> sqrt                        (:207-354)
+//   argmin/argmax: (value, row-major index), first occurrence wins                                          (:356-464)
+//   all/any: && / || over bool        count_nonzero (and sum of bool): usize count                          (:466-715)
 // Float max/min ignore NaN and start from the finite extreme (rstsr-dtype-traits/src/ext_real.rs:70-87);
 // the accumulator has the element type (f32 sums in f32); integer sums wrap.
 //
-//   reduce_rows_kernel  a group of G threads (1..256) owns one output and strides over the reduced index
-//                       space; when the smallest-stride reduced dim is contiguous it is read as 32-byte packs
-//                       (256-bit LDG), 8 packs in flight per thread.  Warp-shuffle tree inside a warp,
-//                       shared-memory tree across warps.
-//   reduce_cols_kernel  the kept fastest axis is contiguous in input and output: lanes own columns
-//                       (32-byte packs), warps walk the reduced rows: coalesced 1 KiB per warp and row.
-// Both take a split factor S along the reduced space (gridDim.y); S > 1 writes partials[S][n_out] into the
-// device handle's workspace and a second launch of the same kernel folds them in a FIXED order: the result
-// is run-to-run deterministic (no float atomics), which the reference's rayon fold is not.
+// A reduction is a POLICY {TI element, S state, TO output; init, pre(x, idx) -> S, comb(S, S), fin(S, n) -> TO}.
+//   reduce_rows_kernel<P>  a group of G threads (1..256) owns one output and strides over the reduced index
+//                          space; when the smallest-stride reduced dim is contiguous it is read as 32-byte packs
+//                          (256-bit LDG), 8 packs in flight per thread.  Shuffle tree in a warp, smem tree across.
+//   reduce_cols_kernel<P>  the kept fastest axis is contiguous in input and output: lanes own columns
+//                          (32-byte packs), warps walk the reduced rows: coalesced >= 1 KiB per warp and row.
+// Both take a split factor S along the reduced space (gridDim.y); S > 1 writes partial STATES[S][n_out] into the
+// device handle's workspace and a second launch folds them in a FIXED order: results are run-to-run
+// deterministic (no float atomics), which the reference's rayon fold is not.
 //
 // Measured on B200 (scripts/membench.cu): a read-only stream needs >= 128 KB in flight per SM to reach
 // 6.7-7.0 TB/s; 256-bit loads x 8 per thread do, 128-bit x 4 stall at 6.1 TB/s.
@@ -42,53 +46,133 @@ struct RedDesc {
     int64_t chunk;              // reduced items per split
     int64_t n_out_total;        // elements of the output (partial row pitch)
     int64_t packs0;             // cols kernel: packs along kept dim 0
+    int64_t n_red;              // reduced element count (mean / var divisor)
     int group;                  // rows kernel: threads per output
     int tcol;                   // cols kernel: threads along the kept axis
-    int do_div;                 // mean: divide by div on the final write
-    int to_partial;             // write un-finalised accumulators to the partial buffer
+    int to_partial;             // write un-finalised states to the partial buffer
 };
 
-template <class T> struct OpSum {
-    static __device__ __forceinline__ T init() { return (T)0; }
-    static __device__ __forceinline__ T f(T a, T b) {
-        if constexpr (std::is_integral<T>::value) return (T)((typename std::make_unsigned<T>::type)a + (typename std::make_unsigned<T>::type)b);
-        else return a + b;
+template <class T> using uns = typename std::make_unsigned<T>::type;
+
+// ---------------- policies ----------------
+template <class T> struct PSum {
+    using TI = T; using S = T; using TO = T; using Second = PSum<T>;
+    static __device__ __forceinline__ S init() { return (T)0; }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x; }
+    static __device__ __forceinline__ S comb(S a, S b) {
+        if constexpr (std::is_integral<T>::value) return (T)((uns<T>)a + (uns<T>)b); else return a + b;
     }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
 };
-template <class T> struct OpProd {
-    static __device__ __forceinline__ T init() { return (T)1; }
-    static __device__ __forceinline__ T f(T a, T b) {
-        if constexpr (std::is_integral<T>::value) return (T)((typename std::make_unsigned<T>::type)a * (typename std::make_unsigned<T>::type)b);
-        else return a * b;
+template <class T> struct PMean {
+    using TI = T; using S = T; using TO = T; using Second = PMean<T>;
+    static __device__ __forceinline__ S init() { return (T)0; }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x; }
+    static __device__ __forceinline__ S comb(S a, S b) { return a + b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t n) { return s / (T)n; }  // T::from_usize(n)
+};
+template <class T> struct PProd {
+    using TI = T; using S = T; using TO = T; using Second = PProd<T>;
+    static __device__ __forceinline__ S init() { return (T)1; }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x; }
+    static __device__ __forceinline__ S comb(S a, S b) {
+        if constexpr (std::is_integral<T>::value) return (T)((uns<T>)a * (uns<T>)b); else return a * b;
     }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
 };
-template <class T> struct OpMax {
-    static __device__ __forceinline__ T init() { return std::numeric_limits<T>::lowest(); }
-    static __device__ __forceinline__ T f(T a, T b) {
+template <class T> struct PMax {
+    using TI = T; using S = T; using TO = T; using Second = PMax<T>;
+    static __device__ __forceinline__ S init() { return std::numeric_limits<T>::lowest(); }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x; }
+    static __device__ __forceinline__ S comb(S a, S b) {
         if constexpr (std::is_same<T, float>::value) return fmaxf(a, b);
         else if constexpr (std::is_same<T, double>::value) return fmax(a, b);
         else return a < b ? b : a;
     }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
 };
-template <class T> struct OpMin {
-    static __device__ __forceinline__ T init() { return std::numeric_limits<T>::max(); }
-    static __device__ __forceinline__ T f(T a, T b) {
+template <class T> struct PMin {
+    using TI = T; using S = T; using TO = T; using Second = PMin<T>;
+    static __device__ __forceinline__ S init() { return std::numeric_limits<T>::max(); }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x; }
+    static __device__ __forceinline__ S comb(S a, S b) {
         if constexpr (std::is_same<T, float>::value) return fminf(a, b);
         else if constexpr (std::is_same<T, double>::value) return fmin(a, b);
         else return b < a ? b : a;
     }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
 };
 
-template <class T>
-__device__ __forceinline__ T finalize(T acc, int do_div, T div) {
-    if constexpr (std::is_floating_point<T>::value) {
-        if (do_div) return acc / div;
-    }
-    return acc;
-}
+// second pass over already-reduced states of policy P
+template <class P> struct PState {
+    using TI = typename P::S; using S = typename P::S; using TO = typename P::TO; using Second = PState<P>;
+    static __device__ __forceinline__ S init() { return P::init(); }
+    static __device__ __forceinline__ S pre(S x, int64_t) { return x; }
+    static __device__ __forceinline__ S comb(S a, S b) { return P::comb(a, b); }
+    static __device__ __forceinline__ TO fin(S s, int64_t n) { return P::fin(s, n); }
+};
 
-// offset of linear index `i` over dims [first, n) with the given strides (cold path: kept never inlined in
-// the streaming loop unless the reduced space really is multi-dimensional)
+template <class T> struct PL2 {  // l2_norm: f = acc + x*x, f_out = sqrt (auto_impl/reduction.rs:319-354)
+    using TI = T; using S = T; using TO = T; using Second = PState<PL2<T>>;
+    static __device__ __forceinline__ S init() { return (T)0; }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x * x; }
+    static __device__ __forceinline__ S comb(S a, S b) { return a + b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { if constexpr (sizeof(T) == 4) return sqrtf(s); else return sqrt(s); }
+};
+
+template <class T> struct alignas(2 * sizeof(T)) Pair { T s, q; };
+template <class T, bool STD> struct PVar {  // (sum, sum of squares) -> q/n - (s/n)^2 (auto_impl/reduction.rs:207-317)
+    using TI = T; using S = Pair<T>; using TO = T; using Second = PState<PVar<T, STD>>;
+    static __device__ __forceinline__ S init() { return S{(T)0, (T)0}; }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return S{x, x * x}; }
+    static __device__ __forceinline__ S comb(S a, S b) { return S{a.s + b.s, a.q + b.q}; }
+    static __device__ __forceinline__ TO fin(S v, int64_t n) {
+        const T mean = v.s / (T)n;
+        const T var = v.q / (T)n - mean * mean;
+        if constexpr (!STD) return var;
+        else if constexpr (sizeof(T) == 4) return sqrtf(var);
+        else return sqrt(var);
+    }
+};
+
+template <class T> struct PCount {  // count_nonzero / sum of bool -> usize (auto_impl/reduction.rs:522-570,678-715)
+    using TI = T; using S = uint64_t; using TO = uint64_t; using Second = PState<PCount<T>>;
+    static __device__ __forceinline__ S init() { return 0; }
+    static __device__ __forceinline__ S pre(T x, int64_t) { return x != (T)0 ? 1 : 0; }
+    static __device__ __forceinline__ S comb(S a, S b) { return a + b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
+};
+template <bool ALL> struct PLogic {  // all / any over bool (auto_impl/reduction.rs:466-520)
+    using TI = uint8_t; using S = uint8_t; using TO = uint8_t; using Second = PLogic<ALL>;
+    static __device__ __forceinline__ S init() { return ALL ? 1 : 0; }
+    static __device__ __forceinline__ S pre(uint8_t x, int64_t) { return x ? 1 : 0; }
+    static __device__ __forceinline__ S comb(S a, S b) { return ALL ? (a & b) : (a | b); }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
+};
+
+template <class T> struct alignas(16) ArgState { T v; int64_t i; };  // i < 0: empty ("None")
+// argmin / argmax: first occurrence in row-major order wins; NaN is never accepted unless it is element 0
+// (f_comp(None, y) = true, y < NaN = false: cpu_serial/reduction.rs:436-470) -- reproduced order-independently.
+template <class T, bool MAX> struct PArg {
+    using TI = T; using S = ArgState<T>; using TO = uint64_t; using Second = PState<PArg<T, MAX>>;
+    static __device__ __forceinline__ bool isnan_(T x) { return x != x; }
+    static __device__ __forceinline__ S init() { return S{(T)0, -1}; }
+    static __device__ __forceinline__ S pre(T x, int64_t idx) { return (isnan_(x) && idx != 0) ? S{(T)0, -1} : S{x, idx}; }
+    static __device__ __forceinline__ S comb(S a, S b) {
+        if (a.i < 0) return b;
+        if (b.i < 0) return a;
+        if (isnan_(a.v)) return a;  // only global element 0 can carry NaN: it sticks
+        if (isnan_(b.v)) return b;
+        const bool b_better = MAX ? (b.v > a.v) : (b.v < a.v);
+        const bool a_better = MAX ? (a.v > b.v) : (a.v < b.v);
+        if (b_better) return b;
+        if (a_better) return a;
+        return (b.i < a.i) ? b : a;
+    }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return (uint64_t)s.i; }
+};
+
+// offset of linear index `i` over dims [first, n) with the given strides (cold path)
 __device__ __noinline__ int64_t decompose_big(int64_t i, int first, int n, const int64_t *shape, const int64_t *stride) {
     int64_t off = 0;
     for (int k = first; k < n; ++k) {
@@ -115,31 +199,40 @@ __device__ __forceinline__ int64_t decompose(int64_t i, int first, int n, const 
     return off;
 }
 
-template <class T>
-__device__ __forceinline__ T shfl_xor_t(T v, int m) {
-    if constexpr (sizeof(T) == 8) {
-        long long x = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long *>(&v), m);
-        return *reinterpret_cast<T *>(&x);
+template <class S>
+__device__ __forceinline__ S shfl_xor_state(S v, int m) {
+    if constexpr (sizeof(S) < 4) {
+        int x = (int)v;
+        x = __shfl_xor_sync(0xffffffffu, x, m);
+        return (S)x;
     } else {
-        int x = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<int *>(&v), m);
-        return *reinterpret_cast<T *>(&x);
+        static_assert(sizeof(S) % 4 == 0, "state size");
+        S r;
+        const int *src = reinterpret_cast<const int *>(&v);
+        int *dst = reinterpret_cast<int *>(&r);
+#pragma unroll
+        for (int w = 0; w < (int)(sizeof(S) / 4); ++w) dst[w] = __shfl_xor_sync(0xffffffffu, src[w], m);
+        return r;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // MULTI: the reduced index space has more than one (non-mergeable) dim -> per-item decomposition.
-template <class Op, class T, int VEC, bool MULTI>
-__global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_constant__ RedDesc d, const T *__restrict__ in,
-                                                                T *__restrict__ out, T *__restrict__ partial,
-                                                                T div) {
-    __shared__ T warp_acc[RED_BLOCK / 32];
+template <class P, int VEC, bool MULTI>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_constant__ RedDesc d,
+                                                                const typename P::TI *__restrict__ in,
+                                                                typename P::TO *__restrict__ out,
+                                                                typename P::S *__restrict__ partial) {
+    using TI = typename P::TI;
+    using S = typename P::S;
+    __shared__ S warp_acc[RED_BLOCK / 32];
     const int G = d.group;
     const int tid = threadIdx.x;
     const int g = tid / G, t = tid - g * G;
     const int64_t o = (int64_t)blockIdx.x * (RED_BLOCK / G) + g;
     const bool valid = o < d.n_out;
     int64_t off_out = 0;
-    const T *src = in;
+    const TI *src = in;
     if (valid) {
         src += decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
         off_out = decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
@@ -149,67 +242,71 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
     if (end > d.n_items) end = d.n_items;
     if (!valid) end = begin;
 
-    T acc[VEC];
+    S acc[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = Op::init();
+    for (int j = 0; j < VEC; ++j) acc[j] = P::init();
 
     const int64_t rs0 = d.rs[0];  // per item (already multiplied by VEC for packs)
     int64_t i = begin + t;
     // full groups: RED_UNROLL independent loads in flight, no per-load predicate
     for (; i + (int64_t)(RED_UNROLL - 1) * G < end; i += (int64_t)G * RED_UNROLL) {
-        Pack<T, VEC> p[RED_UNROLL];
+        Pack<TI, VEC> p[RED_UNROLL];
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u) {
             const int64_t ii = i + (int64_t)u * G;
             int64_t off;
             if constexpr (MULTI) off = decompose(ii, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
             else off = ii * rs0;
-            p[u] = ld_stream<T, VEC>(src + off);
+            p[u] = ld_stream<TI, VEC>(src + off);
         }
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p[u].v[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p[u].v[j], (i + (int64_t)u * G) * VEC + j));
     }
     for (; i < end; i += G) {
         int64_t off;
         if constexpr (MULTI) off = decompose(i, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
         else off = i * rs0;
-        Pack<T, VEC> p = ld_stream<T, VEC>(src + off);
+        Pack<TI, VEC> p = ld_stream<TI, VEC>(src + off);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p.v[j]);
+        for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], i * VEC + j));
     }
     // fold the pack lanes, then the group, in a fixed order
-    T v = acc[0];
+    S v = acc[0];
 #pragma unroll
-    for (int j = 1; j < VEC; ++j) v = Op::f(v, acc[j]);
+    for (int j = 1; j < VEC; ++j) v = P::comb(v, acc[j]);
 
     if (G <= 32) {
-        for (int m = G >> 1; m >= 1; m >>= 1) v = Op::f(v, shfl_xor_t<T>(v, m));
+        for (int m = G >> 1; m >= 1; m >>= 1) v = P::comb(v, shfl_xor_state<S>(v, m));
     } else {
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) v = Op::f(v, shfl_xor_t<T>(v, m));
+        for (int m = 16; m >= 1; m >>= 1) v = P::comb(v, shfl_xor_state<S>(v, m));
         if ((tid & 31) == 0) warp_acc[tid >> 5] = v;
         __syncthreads();
         if (t == 0) {
             const int w0 = tid >> 5, nw = G >> 5;
             v = warp_acc[w0];
-            for (int w = 1; w < nw; ++w) v = Op::f(v, warp_acc[w0 + w]);
+            for (int w = 1; w < nw; ++w) v = P::comb(v, warp_acc[w0 + w]);
         }
     }
     if (valid && t == 0) {
         if (d.to_partial) partial[(int64_t)blockIdx.y * d.n_out_total + o] = v;
-        else out[off_out] = finalize<T>(v, d.do_div, div);
+        else out[off_out] = P::fin(v, d.n_red);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <class Op, class T, int VEC, bool MULTI>
-__global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_constant__ RedDesc d, const T *__restrict__ in,
-                                                                T *__restrict__ out, T *__restrict__ partial,
-                                                                T div) {
+template <class P, int VEC, bool MULTI>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_constant__ RedDesc d,
+                                                                const typename P::TI *__restrict__ in,
+                                                                typename P::TO *__restrict__ out,
+                                                                typename P::S *__restrict__ partial) {
+    using TI = typename P::TI;
+    using S = typename P::S;
+    using TO = typename P::TO;
     extern __shared__ __align__(32) unsigned char red_smem[];
-    Pack<T, VEC> *sm = reinterpret_cast<Pack<T, VEC> *>(red_smem);
+    S *sm = reinterpret_cast<S *>(red_smem);  // [RW][TC][VEC]
     const int TC = d.tcol, RW = RED_BLOCK / TC;
     const int tx = threadIdx.x % TC, ty = threadIdx.x / TC;
     const int64_t ntile0 = (d.packs0 + TC - 1) / TC;
@@ -218,7 +315,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
     const int64_t col = (tile - kb * ntile0) * TC + tx;  // pack index along kept dim 0
     const bool valid = col < d.packs0;
     int64_t off_out = 0;
-    const T *src = in;
+    const TI *src = in;
     if (valid) {
         src += col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
         off_out = col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
@@ -228,55 +325,57 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
     if (end > d.n_items) end = d.n_items;
     if (!valid) end = begin;
 
-    T acc[VEC];
+    S acc[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = Op::init();
+    for (int j = 0; j < VEC; ++j) acc[j] = P::init();
 
     const int64_t rs0 = d.rs[0];
     int64_t r = begin + ty;
     for (; r + (int64_t)(RED_UNROLL - 1) * RW < end; r += (int64_t)RW * RED_UNROLL) {
-        Pack<T, VEC> p[RED_UNROLL];
+        Pack<TI, VEC> p[RED_UNROLL];
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u) {
             const int64_t rr = r + (int64_t)u * RW;
             int64_t off;
             if constexpr (MULTI) off = decompose(rr, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
             else off = rr * rs0;
-            p[u] = ld_stream<T, VEC>(src + off);
+            p[u] = ld_stream<TI, VEC>(src + off);
         }
 #pragma unroll
         for (int u = 0; u < RED_UNROLL; ++u)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p[u].v[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p[u].v[j], r + (int64_t)u * RW));
     }
     for (; r < end; r += RW) {
         int64_t off;
         if constexpr (MULTI) off = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
         else off = r * rs0;
-        Pack<T, VEC> p = ld_stream<T, VEC>(src + off);
+        Pack<TI, VEC> p = ld_stream<TI, VEC>(src + off);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = Op::f(acc[j], p.v[j]);
+        for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], r));
     }
-    Pack<T, VEC> v;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) v.v[j] = acc[j];
-    sm[ty * TC + tx] = v;
+    for (int j = 0; j < VEC; ++j) sm[(ty * TC + tx) * VEC + j] = acc[j];
     __syncthreads();
     if (ty == 0 && valid) {
         for (int w = 1; w < RW; ++w) {
-            Pack<T, VEC> o = sm[w * TC + tx];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) v.v[j] = Op::f(v.v[j], o.v[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], sm[(w * TC + tx) * VEC + j]);
         }
         if (d.to_partial) {
-            T *dst = partial + (int64_t)blockIdx.y * d.n_out_total + kb * (d.packs0 * VEC) + col * VEC;
-            if (VEC > 1) st_stream<T, VEC>(dst, v);
-            else dst[0] = v.v[0];
-        } else {
+            S *dst = partial + (int64_t)blockIdx.y * d.n_out_total + kb * (d.packs0 * VEC) + col * VEC;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) v.v[j] = finalize<T>(v.v[j], d.do_div, div);
-            if (VEC > 1) st_stream<T, VEC>(out + off_out, v);
-            else out[off_out] = v.v[0];
+            for (int j = 0; j < VEC; ++j) dst[j] = acc[j];
+        } else {
+            Pack<TO, VEC> o;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o.v[j] = P::fin(acc[j], d.n_red);
+            if constexpr (VEC > 1 && (VEC * sizeof(TO) == 16 || VEC * sizeof(TO) == 32)) {
+                st_stream<TO, VEC>(out + off_out, o);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) out[off_out + j] = o.v[j];
+            }
         }
     }
 }
@@ -303,42 +402,51 @@ void fill_desc_dims(RedDesc &d, const CanonRed &c) {
     }
 }
 
-template <class T>
-bool aligned_for(const void *p, int vec) { return reinterpret_cast<uintptr_t>(p) % (vec * sizeof(T)) == 0; }
+inline bool aligned_bytes(const void *p, size_t bytes) { return reinterpret_cast<uintptr_t>(p) % bytes == 0; }
 
-template <class Op, class T>
-void launch_rows(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const T *in, T *out, T *partial, T div) {
+template <class P, int V>
+void launch_rows(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const typename P::TI *in, typename P::TO *out,
+                 typename P::S *partial) {
     int64_t gx = (d.n_out + (RED_BLOCK / d.group) - 1) / (RED_BLOCK / d.group);
     RC_CHECK(gx < (1ll << 31) && sy <= 65535, RC_ERR_UNIMPLEMENTED, "reduction grid too large");
     dim3 grid((unsigned)gx, (unsigned)sy);
-    constexpr int V = 32 / sizeof(T);
     const bool multi = d.nr > 1;
-    if (vec > 1) {
-        if (multi) reduce_rows_kernel<Op, T, V, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
-        else reduce_rows_kernel<Op, T, V, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
-    } else {
-        if (multi) reduce_rows_kernel<Op, T, 1, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
-        else reduce_rows_kernel<Op, T, 1, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial, div);
+    if constexpr (V > 1) {
+        if (vec > 1) {
+            if (multi) reduce_rows_kernel<P, V, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
+            else reduce_rows_kernel<P, V, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
+            after_launch(dev, "reduce_rows_kernel");
+            return;
+        }
     }
+    if (multi) reduce_rows_kernel<P, 1, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
+    else reduce_rows_kernel<P, 1, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
     after_launch(dev, "reduce_rows_kernel");
 }
 
-template <class Op, class T>
-void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const T *in, T *out, T *partial, T div) {
+template <class P, int V>
+void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const typename P::TI *in, typename P::TO *out,
+                 typename P::S *partial) {
     int64_t ntile0 = (d.packs0 + d.tcol - 1) / d.tcol;
     int64_t gx = ntile0 * d.n_out;
     RC_CHECK(gx < (1ll << 31) && sy <= 65535, RC_ERR_UNIMPLEMENTED, "reduction grid too large");
     dim3 grid((unsigned)gx, (unsigned)sy);
-    constexpr int V = 32 / sizeof(T);
-    size_t smem = (size_t)RED_BLOCK * sizeof(T) * (vec > 1 ? V : 1);
+    size_t smem = (size_t)RED_BLOCK * sizeof(typename P::S) * (vec > 1 ? V : 1);
     const bool multi = d.nr > 1;
-    if (vec > 1) {
-        if (multi) reduce_cols_kernel<Op, T, V, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
-        else reduce_cols_kernel<Op, T, V, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
-    } else {
-        if (multi) reduce_cols_kernel<Op, T, 1, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
-        else reduce_cols_kernel<Op, T, 1, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial, div);
+    if constexpr (V > 1) {
+        if (vec > 1) {
+            if (smem > 48 * 1024) {  // wide packs of a narrow element with a wide state (bool -> u64 counts)
+                RC_CUDA(cudaFuncSetAttribute(reduce_cols_kernel<P, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                RC_CUDA(cudaFuncSetAttribute(reduce_cols_kernel<P, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            if (multi) reduce_cols_kernel<P, V, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
+            else reduce_cols_kernel<P, V, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
+            after_launch(dev, "reduce_cols_kernel");
+            return;
+        }
     }
+    if (multi) reduce_cols_kernel<P, 1, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
+    else reduce_cols_kernel<P, 1, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
     after_launch(dev, "reduce_cols_kernel");
 }
 
@@ -351,16 +459,19 @@ inline int tcol_max() {
 int pow2_floor(int64_t x) { int p = 1; while ((int64_t)p * 2 <= x) p *= 2; return p; }
 int pow2_ceil(int64_t x) { int p = 1; while (p < x) p *= 2; return p; }
 
-template <class Op, class T>
-void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, bool mean, int64_t mean_count) {
+// P: first-pass policy.  The second pass (over partial states) uses P::Second (P itself when pre is the identity).
+template <class P>
+void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, int64_t n_red_logical) {
+    using TI = typename P::TI;
+    using S = typename P::S;
+    using TO = typename P::TO;
+    using P2 = typename P::Second;
     if (c.empty_out) return;
-    const T *in = static_cast<const T *>(a_v) + c.base_in;
-    T *out = static_cast<T *>(out_v) + c.base_out;
-    T div = (T)1;
-    if (mean) div = (T)mean_count;  // T::from_usize(n) (auto_impl/reduction.rs:181,199)
-    constexpr int V = 32 / sizeof(T);
+    const TI *in = static_cast<const TI *>(a_v) + c.base_in;
+    TO *out = static_cast<TO *>(out_v) + c.base_out;
+    constexpr int V = 32 / sizeof(TI);        // 256-bit packs of the element type
+    constexpr bool SIMPLE = std::is_same<P2, P>::value;  // state == element, pre == identity
     const int64_t n_out = c.n_out(), n_red = c.n_red();
-    // 2 resident CTAs per SM keep 2 x 256 threads x 8 x 32 B = 128 KB in flight; aim for >= 4 waves of work
     // two FULL waves at the kernels' occupancy (4 CTAs of 256 threads per SM at <= 64 registers): a split that
     // overshoots a wave boundary leaves a tail wave (measured: 1280 vs 1184 CTAs costs 4 %)
     const int64_t target_ctas = (int64_t)dev->sm_count * 8;
@@ -368,16 +479,30 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     RedDesc d;
     std::memset(&d, 0, sizeof(d));
     fill_desc_dims(d, c);
-    d.do_div = mean ? 1 : 0;
+    d.n_red = n_red_logical;
     d.n_out_total = n_out;
     if (n_out >= (1ll << 31)) d.big = 1;
 
     const bool red_contig = d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] >= 8;
     const bool kept_contig = d.nk >= 1 && d.ks_in[0] == 1 && d.ks_out[0] == 1 && d.kshape[0] >= 8;
 
+    auto second_pass_desc = [&](const RedDesc &first, int64_t Sx) {
+        RedDesc e = first;
+        e.to_partial = 0;
+        e.nr = 1;
+        e.rshape[0] = Sx;
+        e.rs[0] = n_out;
+        e.rdiv[0] = FastDiv((uint32_t)Sx);
+        int64_t acc = 1;
+        for (int i = 0; i < e.nk; ++i) { e.ks_in[i] = acc; acc *= e.kshape[i]; }
+        e.n_items = Sx;
+        e.chunk = Sx;
+        return e;
+    };
+
     if (!red_contig && kept_contig && n_red > 0) {
         // ---------------- column kernel ----------------
-        bool vec_ok = d.kshape[0] % V == 0 && aligned_for<T>(in, V) && aligned_for<T>(out, V);
+        bool vec_ok = V > 1 && d.kshape[0] % V == 0 && aligned_bytes(in, 32) && aligned_bytes(out, V * sizeof(TO));
         for (int i = 1; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0 && d.ks_out[i] % V == 0;
         for (int i = 0; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
         const int vec = vec_ok ? V : 1;
@@ -388,40 +513,32 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         if (n_red >= (1ll << 31) || d.n_out >= (1ll << 31)) d.big = 1;
         const int rw = RED_BLOCK / d.tcol;
         int64_t base_ctas = ((d.packs0 + d.tcol - 1) / d.tcol) * d.n_out;
-        int64_t S = std::min<int64_t>(std::max<int64_t>(1, target_ctas / base_ctas),
-                                      std::max<int64_t>(1, n_red / ((int64_t)rw * RED_UNROLL * 2)));
-        S = std::max<int64_t>(1, std::min<int64_t>(S, 1024));
-        d.chunk = (n_red + S - 1) / S;
-        S = (n_red + d.chunk - 1) / d.chunk;
-        if (S == 1) {
+        int64_t Sx = std::min<int64_t>(std::max<int64_t>(1, target_ctas / base_ctas),
+                                       std::max<int64_t>(1, n_red / ((int64_t)rw * RED_UNROLL * 2)));
+        Sx = std::max<int64_t>(1, std::min<int64_t>(Sx, 1024));
+        d.chunk = (n_red + Sx - 1) / Sx;
+        Sx = (n_red + d.chunk - 1) / d.chunk;
+        if (Sx == 1) {
             d.to_partial = 0;
-            launch_cols<Op, T>(dev, d, vec, 1, in, out, (T *)nullptr, div);
+            launch_cols<P, V>(dev, d, vec, 1, in, out, (S *)nullptr);
             return;
         }
-        T *partial = static_cast<T *>(workspace(dev, (size_t)S * n_out * sizeof(T)));
+        S *partial = static_cast<S *>(workspace(dev, (size_t)Sx * n_out * sizeof(S)));
         d.to_partial = 1;
-        launch_cols<Op, T>(dev, d, vec, S, in, out, partial, div);
+        launch_cols<P, V>(dev, d, vec, Sx, in, out, partial);
         // second pass: fold partial[S][n_out] over S, same kept dims with contiguous input strides
-        RedDesc e = d;
-        e.to_partial = 0;
-        e.nr = 1;
-        e.rshape[0] = S;
-        e.rs[0] = n_out;
-        e.rdiv[0] = FastDiv((uint32_t)S);
-        int64_t acc = 1;
-        for (int i = 0; i < e.nk; ++i) { e.ks_in[i] = acc; acc *= e.kshape[i]; }
-        e.n_items = S;
-        e.chunk = S;
-        const bool vec2 = vec_ok && (n_out % V == 0) && aligned_for<T>(partial, V);
-        const int v2 = vec2 ? V : 1;
+        RedDesc e = second_pass_desc(d, Sx);
+        constexpr int V2 = SIMPLE ? V : 1;
+        const bool vec2 = V2 > 1 && vec_ok && (n_out % V2 == 0) && aligned_bytes(partial, 32);
+        const int v2 = vec2 ? V2 : 1;
         e.packs0 = e.kshape[0] / v2;
         e.tcol = (int)std::min<int64_t>(tcol_max(), pow2_ceil(e.packs0));
-        launch_cols<Op, T>(dev, e, v2, 1, partial, out, (T *)nullptr, div);
+        launch_cols<P2, V2>(dev, e, v2, 1, partial, out, (S *)nullptr);
         return;
     }
 
     // ---------------- row kernel (contiguous or generic reduced space) ----------------
-    bool vec_ok = d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_for<T>(in, V);
+    bool vec_ok = V > 1 && d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_bytes(in, 32);
     for (int i = 0; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0;
     for (int i = 1; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
     const int vec = vec_ok ? V : 1;
@@ -441,54 +558,67 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     if (d.n_items >= (1ll << 31) && d.nr > 1) d.big = 1;
     d.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, d.n_items / RED_UNROLL))));
     int64_t base_ctas = (n_out + (RED_BLOCK / d.group) - 1) / (RED_BLOCK / d.group);
-    int64_t S = 1;
+    int64_t Sx = 1;
     if (base_ctas < target_ctas) {
-        S = std::min<int64_t>(std::max<int64_t>(1, target_ctas / base_ctas),
-                              std::max<int64_t>(1, d.n_items / ((int64_t)d.group * RED_UNROLL * 4)));
-        S = std::max<int64_t>(1, std::min<int64_t>(S, 4096));
+        Sx = std::min<int64_t>(std::max<int64_t>(1, target_ctas / base_ctas),
+                               std::max<int64_t>(1, d.n_items / ((int64_t)d.group * RED_UNROLL * 4)));
+        Sx = std::max<int64_t>(1, std::min<int64_t>(Sx, 4096));
     }
-    d.chunk = (d.n_items + S - 1) / std::max<int64_t>(S, 1);
+    d.chunk = (d.n_items + Sx - 1) / std::max<int64_t>(Sx, 1);
     if (d.chunk == 0) d.chunk = 1;
-    S = std::max<int64_t>(1, (d.n_items + d.chunk - 1) / d.chunk);
-    if (S == 1) {
+    Sx = std::max<int64_t>(1, (d.n_items + d.chunk - 1) / d.chunk);
+    if (Sx == 1) {
         d.to_partial = 0;
-        launch_rows<Op, T>(dev, d, vec, 1, in, out, (T *)nullptr, div);
+        launch_rows<P, V>(dev, d, vec, 1, in, out, (S *)nullptr);
         return;
     }
-    T *partial = static_cast<T *>(workspace(dev, (size_t)S * n_out * sizeof(T)));
+    S *partial = static_cast<S *>(workspace(dev, (size_t)Sx * n_out * sizeof(S)));
     d.to_partial = 1;
-    launch_rows<Op, T>(dev, d, vec, S, in, out, partial, div);
+    launch_rows<P, V>(dev, d, vec, Sx, in, out, partial);
     // second pass: out[o] = fold_s partial[s][o]
-    RedDesc e = d;
-    e.to_partial = 0;
-    e.nr = 1;
-    e.rshape[0] = S;
-    e.rs[0] = n_out;
-    e.rdiv[0] = FastDiv((uint32_t)S);
-    int64_t acc = 1;
-    for (int i = 0; i < e.nk; ++i) { e.ks_in[i] = acc; acc *= e.kshape[i]; }
-    e.n_items = S;
-    e.chunk = S;
-    e.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, S / 2))));
-    launch_rows<Op, T>(dev, e, 1, 1, partial, out, (T *)nullptr, div);
+    RedDesc e = second_pass_desc(d, Sx);
+    e.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, Sx / 2))));
+    launch_rows<P2, 1>(dev, e, 1, 1, partial, out, (S *)nullptr);
 }
 
+// the five monoids of the hot path
 template <class T>
-void reduce_op(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, void *out, int64_t mean_count) {
+void reduce_op(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, void *out, int64_t n_red) {
     switch (op) {
-        case RC_SUM: reduce_typed<OpSum<T>, T>(dev, c, a, out, false, 1); return;
-        case RC_PROD: reduce_typed<OpProd<T>, T>(dev, c, a, out, false, 1); return;
-        case RC_MAX: reduce_typed<OpMax<T>, T>(dev, c, a, out, false, 1); return;
-        case RC_MIN: reduce_typed<OpMin<T>, T>(dev, c, a, out, false, 1); return;
+        case RC_SUM: reduce_typed<PSum<T>>(dev, c, a, out, n_red); return;
+        case RC_PROD: reduce_typed<PProd<T>>(dev, c, a, out, n_red); return;
+        case RC_MAX: reduce_typed<PMax<T>>(dev, c, a, out, n_red); return;
+        case RC_MIN: reduce_typed<PMin<T>>(dev, c, a, out, n_red); return;
         case RC_MEAN:
             if constexpr (std::is_floating_point<T>::value) {
-                reduce_typed<OpSum<T>, T>(dev, c, a, out, true, mean_count);
+                reduce_typed<PMean<T>>(dev, c, a, out, n_red);
                 return;
             } else {
                 raise(RC_ERR_UNIMPLEMENTED, "mean is only defined for floating-point element types");
             }
+        default: break;
     }
     raise(RC_ERR_INVALID_VALUE, "unknown reduction op");
+}
+
+// the "next" reductions: var / std / l2_norm (floats), argmin / argmax, count_nonzero
+template <class T>
+void reduce_op_ext(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, void *out, int64_t n_red) {
+    switch (op) {
+        case RC_ARGMIN: reduce_typed<PArg<T, false>>(dev, c, a, out, n_red); return;
+        case RC_ARGMAX: reduce_typed<PArg<T, true>>(dev, c, a, out, n_red); return;
+        case RC_COUNT_NONZERO: reduce_typed<PCount<T>>(dev, c, a, out, n_red); return;
+        default: break;
+    }
+    if constexpr (std::is_floating_point<T>::value) {
+        switch (op) {
+            case RC_VAR: reduce_typed<PVar<T, false>>(dev, c, a, out, n_red); return;
+            case RC_STD: reduce_typed<PVar<T, true>>(dev, c, a, out, n_red); return;
+            case RC_L2_NORM: reduce_typed<PL2<T>>(dev, c, a, out, n_red); return;
+            default: break;
+        }
+    }
+    raise(RC_ERR_UNIMPLEMENTED, "this reduction is not implemented for the element type");
 }
 
 }  // namespace

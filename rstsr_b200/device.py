@@ -361,8 +361,14 @@ class DeviceCuda:
         return dtype_np(out.value)
 
     # ---- reductions ----
+    @staticmethod
+    def redop_out_dtype(op: str, dtype) -> np.dtype:
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_redop_out_dtype(_ffi.REDOPS[op], dtype_code(dtype), byref(out)))
+        return dtype_np(out.value)
+
     def reduce_all(self, op: str, a: CudaRaw, la: Layout):
-        out = np.empty(1, dtype=a.dtype)
+        out = np.empty(1, dtype=self.redop_out_dtype(op, a.dtype))
         check(_ffi.lib().rc_reduce_all(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
                                        out.ctypes.data))
         return out[0]
@@ -378,7 +384,7 @@ class DeviceCuda:
         check(_ffi.lib().rc_reduce_axes(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()), arr,
                                         len(axes), byref(p), byref(lo)))
         layout = Layout.from_c(lo)
-        return CudaRaw(self, p.value, max(layout.size, 1), a.dtype), layout
+        return CudaRaw(self, p.value, max(layout.size, 1), self.redop_out_dtype(op, a.dtype)), layout
 
     def reduce_axes_into(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int], out: CudaRaw, lo: Layout):
         arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])

@@ -334,6 +334,24 @@ class Tensor:
     def mean_axes(self, axes): return self._reduce("mean", axes)
     sum, prod, max, min, mean = sum_all, prod_all, max_all, min_all, mean_all
 
+    # the "next" reductions (tensor/reduction.rs:118-133): same call shape, other monoids
+    def var_all(self): return self._reduce("var")
+    def std_all(self): return self._reduce("std")
+    def l2_norm_all(self): return self._reduce("l2_norm")
+    def argmin_all(self): return self._reduce("argmin")
+    def argmax_all(self): return self._reduce("argmax")
+    def all_all(self): return bool(self._reduce("all"))
+    def any_all(self): return bool(self._reduce("any"))
+    def count_nonzero_all(self): return self._reduce("count_nonzero")
+    def var_axes(self, axes): return self._reduce("var", axes)
+    def std_axes(self, axes): return self._reduce("std", axes)
+    def l2_norm_axes(self, axes): return self._reduce("l2_norm", axes)
+    def argmin_axes(self, axes): return self._reduce("argmin", axes)
+    def argmax_axes(self, axes): return self._reduce("argmax", axes)
+    def all_axes(self, axes): return self._reduce("all", axes)
+    def any_axes(self, axes): return self._reduce("any", axes)
+    def count_nonzero_axes(self, axes): return self._reduce("count_nonzero", axes)
+
 
 # ---- creation (rstsr-core/src/tensor/{asarray,creation}.rs) ----
 def asarray(data, device: DeviceCuda, layout: Optional[Layout] = None, dtype=None) -> Tensor:

@@ -1,0 +1,145 @@
+"""GPU parity for the "next" reductions: var / std / l2_norm / argmin / argmax / all / any /
+count_nonzero -- same kernels as sum/max with other monoids.  KATs: rstsr-core/src/tensor/reduction.rs:615-909."""
+import numpy as np
+import pytest
+
+import oracle
+import rstsr_b200 as rt
+from oracle import layout as L
+
+from helpers import O, P, rand_data, random_view, same, seed_of, upload, view_np
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_kats(dev):
+    v = np.array([8, 4, 2, 9, 3, 7, 2, 8, 1, 6, 10, 5], dtype=np.float64)
+    a = rt.asarray(v, dev).reshape([4, 3])
+    # tensor/reduction.rs test_var / test_std: np.var / np.std of the same data
+    assert abs(a.var_all() - np.var(v)) < 1e-12
+    assert np.allclose(a.var_axes(0).to_numpy(), np.var(v.reshape(4, 3), axis=0), rtol=1e-12)
+    assert np.allclose(a.var_axes(1).to_numpy(), np.var(v.reshape(4, 3), axis=1), rtol=1e-12)
+    assert abs(a.std_all() - np.std(v)) < 1e-12
+    assert np.allclose(a.std_axes(0).to_numpy(), np.std(v.reshape(4, 3), axis=0), rtol=1e-12)
+    assert abs(a.l2_norm_all() - np.linalg.norm(v)) < 1e-12
+    assert np.allclose(a.l2_norm_axes(0).to_numpy(), np.linalg.norm(v.reshape(4, 3), axis=0), rtol=1e-13)
+    # argmin / argmax (tensor/reduction.rs:816-866): first occurrence, row-major flattened index
+    i = rt.asarray(v.astype(np.int64), dev).reshape([4, 3])
+    assert i.argmin_all() == 8 and i.argmax_all() == 10
+    assert i.argmin_axes(0).to_numpy().tolist() == [2, 1, 2]   # columns: [8,9,2,6] [4,3,8,10] [2,7,1,5]
+    assert i.argmin_axes(1).to_numpy().tolist() == [2, 1, 2, 2]
+    assert i.argmax_axes(0).to_numpy().tolist() == [1, 3, 1]
+    ties = rt.asarray(np.array([3, 1, 1, 3, 1, 3]), dev)
+    assert ties.argmin_all() == 1 and ties.argmax_all() == 0
+    b = rt.asarray(np.array([True, True, False, True]), dev).reshape([2, 2])
+    assert b.all_all() is False and b.any_all() is True
+    assert b.all_axes(0).to_numpy().tolist() == [False, True]
+    assert b.any_axes(1).to_numpy().tolist() == [True, True]
+    assert b.count_nonzero_all() == 3                      # OpSumBoolAPI: sum of a bool tensor
+    z = rt.asarray(np.array([0.0, 1.5, 0.0, -2.0, 0.0, 3.0]), dev).reshape([2, 3])
+    assert z.count_nonzero_all() == 3
+    assert z.count_nonzero_axes(0).to_numpy().tolist() == [1, 1, 1]
+    assert z.count_nonzero_axes(1).to_numpy().tolist() == [1, 2]
+
+
+def test_arg_nan_rule(dev):
+    """y < NaN is false and f_comp(None, y) is true (cpu_serial/reduction.rs:436-470): NaN is skipped unless first."""
+    a = rt.asarray(np.array([2.0, np.nan, 1.0, np.nan, 1.0]), dev)
+    assert a.argmin_all() == 2 and a.argmax_all() == 0
+    a = rt.asarray(np.array([np.nan, 5.0, 1.0]), dev)
+    assert a.argmin_all() == 0 and a.argmax_all() == 0
+    with pytest.raises(rt.RstsrCudaError) as e:
+        rt.asarray(np.zeros(0), dev).argmin_all()
+    assert e.value.kind == "InvalidLayout"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("op", ["var", "std", "l2_norm"])
+def test_float_moments_random_views(dev, op, dtype):
+    rng = np.random.default_rng(seed_of(op, np.dtype(dtype).name))
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    done = 0
+    while done < 20:
+        la, na = random_view(rng, max_ndim=4, max_extent=9)
+        if la.ndim == 0 or la.size == 0:
+            continue
+        a = rand_data(rng, na, dtype)
+        k = int(rng.integers(1, la.ndim + 1))
+        axes = [int(x) for x in rng.permutation(la.ndim)[:k]]
+        raw, lo = dev.reduce_axes(op, upload(dev, a), P(la), axes)
+        ref, lo_ref = oracle.reduce_ext(op, a, la, axes)
+        assert same(lo, lo_ref)
+        got, want = view_np(dev.to_cpu_vec(raw), O(lo)).astype(np.float64), view_np(ref, lo_ref).astype(np.float64)
+        v = view_np(a, la).astype(np.float64)
+        msq = (v * v).mean(axis=tuple(axes))
+        scale = msq if op == "var" else np.sqrt(np.maximum(msq, 1e-300)) * (1 if op == "std" else np.sqrt(v.size))
+        if op == "std":  # d sqrt(x) blows up near 0: compare variances instead
+            assert (np.abs(got * got - want * want) <= 4 * tol * msq + 1e-300).all()
+        else:
+            assert (np.abs(got - want) <= 4 * tol * np.maximum(scale, 1e-300)).all(), (op, la, axes)
+        s_got = dev.reduce_all(op, upload(dev, a), P(la))
+        s_want = oracle.reduce_ext(op, a, la, None)
+        assert abs(float(s_got) - float(s_want)) <= 8 * tol * max(float((v * v).mean()), 1e-300) * (v.size if op == "l2_norm" else 1) + 1e-300 \
+            or abs(float(s_got) ** 2 - float(s_want) ** 2) <= 8 * tol * float((v * v).sum())
+        done += 1
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int64, np.uint32, np.uint64])
+@pytest.mark.parametrize("op", ["argmin", "argmax", "count_nonzero"])
+def test_index_and_count_random_views(dev, op, dtype):
+    rng = np.random.default_rng(seed_of(op, np.dtype(dtype).name))
+    done = 0
+    while done < 25:
+        la, na = random_view(rng, max_ndim=4, max_extent=8)
+        if la.ndim == 0 or la.size == 0:
+            continue
+        a = rand_data(rng, na, dtype)
+        a = (a.astype(np.float64) // 3).astype(dtype) if np.dtype(dtype).kind == "f" else (a // 200).astype(dtype)  # many ties / zeros
+        k = int(rng.integers(1, la.ndim + 1))
+        axes = [int(x) for x in rng.permutation(la.ndim)[:k]]  # order matters for arg*: flattened in the order given
+        raw, lo = dev.reduce_axes(op, upload(dev, a), P(la), axes)
+        ref, lo_ref = oracle.reduce_ext(op, a, la, axes)
+        assert same(lo, lo_ref)
+        assert raw.dtype == np.uint64
+        assert np.array_equal(view_np(dev.to_cpu_vec(raw), O(lo)), view_np(ref, lo_ref)), (op, la, axes)
+        assert dev.reduce_all(op, upload(dev, a), P(la)) == oracle.reduce_ext(op, a, la, None)
+        done += 1
+
+
+@pytest.mark.parametrize("op", ["all", "any", "count_nonzero"])
+def test_bool_reductions_random_views(dev, op):
+    rng = np.random.default_rng(seed_of("bool", op))
+    done = 0
+    while done < 25:
+        la, na = random_view(rng, max_ndim=4, max_extent=8)
+        if la.ndim == 0:
+            continue
+        a = (rng.random(na) < (0.9 if op == "all" else 0.1)).astype(np.bool_)
+        k = int(rng.integers(1, la.ndim + 1))
+        axes = [int(x) for x in rng.permutation(la.ndim)[:k]]
+        raw, lo = dev.reduce_axes(op, upload(dev, a), P(la), axes)
+        ref, lo_ref = oracle.reduce_ext(op, a, la, axes)
+        assert same(lo, lo_ref)
+        assert np.array_equal(view_np(dev.to_cpu_vec(raw), O(lo)), view_np(ref, lo_ref)), (op, la, axes)
+        assert dev.reduce_all(op, upload(dev, a), P(la)) == oracle.reduce_ext(op, a, la, None)
+        done += 1
+
+
+LARGE = [((2048, 4096), [1]), ((4096, 2048), [0]), ((64, 96, 128), [0, 2]), ((1 << 21,), [0])]
+
+
+@pytest.mark.parametrize("shape,axes", LARGE)
+def test_large_shapes_hit_vector_and_split_paths(dev, shape, axes):
+    rng = np.random.default_rng(seed_of("large", shape))
+    a = rng.standard_normal(int(np.prod(shape)))
+    t = rt.asarray(a, dev).reshape(list(shape))
+    an = a.reshape(shape)
+    ax = tuple(axes)
+    assert np.allclose(t.var_axes(axes).to_numpy(), an.var(axis=ax), rtol=1e-9, atol=1e-12)
+    assert np.allclose(t.l2_norm_axes(axes).to_numpy(), np.sqrt((an * an).sum(axis=ax)), rtol=1e-12)
+    moved = np.moveaxis(an, axes, list(range(an.ndim - len(axes), an.ndim)))
+    flat = moved.reshape(moved.shape[:an.ndim - len(axes)] + (-1,))
+    assert np.array_equal(t.argmax_axes(axes).to_numpy(), flat.argmax(-1).astype(np.uint64))
+    assert np.array_equal(t.argmin_axes(axes).to_numpy(), flat.argmin(-1).astype(np.uint64))
+    assert np.array_equal((t.binary("gt", 0.5)).count_nonzero_axes(axes).to_numpy(), (an > 0.5).sum(axis=ax).astype(np.uint64))
+    assert t.argmax_all() == int(an.argmax()) and t.argmin_all() == int(an.argmin())
