@@ -267,6 +267,21 @@ int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc
 int rc_fill(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype tf, const void *fill);
 
 /* ------------------------------------------------------------------------------------------
+ * DeviceCreationArangeAPI / ComplexFloatAPI (linspace) / TriAPI (rstsr-core/src/storage/creation.rs:41-62;
+ * auto_impl/creation.rs:74-119; loops cpu_rayon/creation.rs:8-131, cpu_serial/op_tri.rs:524-590).
+ * arange / linspace: the CALLEE allocates (free with rc_free); scalars are host values of `dtype`.
+ * arange length and values follow the reference: floats via f64 arithmetic start + i*step, n = ceil((end-start)/step)
+ * with a last element on/past `end` dropped; integers via isize arithmetic.  tril / triu zero the other triangle
+ * of the last two axes IN PLACE (k-th diagonal kept), batched over the leading axes.
+ * ---------------------------------------------------------------------------------------- */
+int rc_arange(rc_device *dev, rc_dtype dtype, const void *start, const void *end, const void *step, void **out_dev,
+              int64_t *n_out);
+int rc_linspace(rc_device *dev, rc_dtype dtype, const void *start, const void *end, int64_t n, int endpoint,
+                void **out_dev);
+int rc_tril(rc_device *dev, rc_dtype dtype, void *a, const rc_layout *la, int64_t k);
+int rc_triu(rc_device *dev, rc_dtype dtype, void *a, const rc_layout *la, int64_t k);
+
+/* ------------------------------------------------------------------------------------------
  * Elementwise (auto_impl/op_ternary_arithmetic.rs, op_ternary_common.rs, op_binary_arithmetic.rs,
  * op_binary_common.rs; loops cpu_rayon/op_with_func.rs:13-390).
  * `dtype` is the operand type TA = TB; the output type is `dtype`, except RC_BOOL for comparisons /

@@ -96,6 +96,10 @@ SIGNATURES = {
     "rc_assign": (c_int, [_P, c_int, _P, _L, c_int, _P, _L]),
     "rc_assign_arbitary": (c_int, [_P, c_int, _P, _L, c_int, _P, _L]),
     "rc_fill": (c_int, [_P, c_int, _P, _L, c_int, _P]),
+    "rc_arange": (c_int, [_P, c_int, _P, _P, _P, POINTER(_P), POINTER(c_int64)]),
+    "rc_linspace": (c_int, [_P, c_int, _P, _P, c_int64, c_int, POINTER(_P)]),
+    "rc_tril": (c_int, [_P, c_int, _P, _L, c_int64]),
+    "rc_triu": (c_int, [_P, c_int, _P, _L, c_int64]),
     "rc_op_mutc_refa_refb": (c_int, [_P, c_int, c_int, _P, _L, _P, _L, _P, _L]),
     "rc_op_mutc_refa_numb": (c_int, [_P, c_int, c_int, _P, _L, _P, _L, _P]),
     "rc_op_mutc_numa_refb": (c_int, [_P, c_int, c_int, _P, _L, _P, _P, _L]),

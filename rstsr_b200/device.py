@@ -249,6 +249,29 @@ class DeviceCuda:
     def ones_impl(self, dtype, length: int) -> CudaRaw:
         return self.full_impl(dtype, length, 1)
 
+    # ---- DeviceCreationArangeAPI / linspace / TriAPI (storage/creation.rs:41-62) ----
+    def arange_impl(self, start, end, step, dtype) -> CudaRaw:
+        dt = np.dtype(dtype)
+        s, e, st = (np.array([v], dtype=dt) for v in (start, end, step))
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        check(_ffi.lib().rc_arange(self._handle, dtype_code(dt), s.ctypes.data, e.ctypes.data, st.ctypes.data, byref(p),
+                                   byref(n)))
+        return CudaRaw(self, p.value, n.value, dt)
+
+    def linspace_impl(self, start, end, n: int, endpoint: bool, dtype) -> CudaRaw:
+        dt = np.dtype(dtype)
+        s, e = np.array([start], dtype=dt), np.array([end], dtype=dt)
+        p = ctypes.c_void_p()
+        check(_ffi.lib().rc_linspace(self._handle, dtype_code(dt), s.ctypes.data, e.ctypes.data, int(n),
+                                     1 if endpoint else 0, byref(p)))
+        return CudaRaw(self, p.value, int(n), dt)
+
+    def tril_impl(self, raw: CudaRaw, layout: Layout, k: int = 0):
+        check(_ffi.lib().rc_tril(self._handle, dtype_code(raw.dtype), raw.ptr, byref(layout.to_c()), int(k)))
+
+    def triu_impl(self, raw: CudaRaw, layout: Layout, k: int = 0):
+        check(_ffi.lib().rc_triu(self._handle, dtype_code(raw.dtype), raw.ptr, byref(layout.to_c()), int(k)))
+
     def outof_cpu_vec(self, vec: np.ndarray) -> CudaRaw:
         vec = np.ascontiguousarray(vec).reshape(-1)
         raw = self.uninit_impl(vec.dtype, vec.size)
