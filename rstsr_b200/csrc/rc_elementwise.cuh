@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_kernel(const __grid_constant__ Ew
 // ---------------------------------------------------------------------------------------------
 // two-dim kernel: dim 0 (packs) x dim 1 (rows).  A CTA owns one 1024-pack chunk of dim 0 and walks R rows.
 // Operands that are broadcast over dim 1 (stride 0: `(8192,8192) + (8192,)`, `a * v`) are loaded ONCE per
-// CTA and stay in registers for all R rows -- re-reading them per row costs a full L2->SM stream and caps the
-// kernel at the L2 fabric limit (measured: 4.3 TB/s instead of 6.5+).  No per-item division at all.
+// CTA and stay in registers for all R rows (R is 1 by default, see the launcher: one-shot grids measured
+// fastest).  No per-item division at all (one fast division per CTA).
 // ---------------------------------------------------------------------------------------------
 struct EwRowsDesc {
     uint32_t n0;              // packs along dim 0
@@ -527,7 +527,11 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                     if (k > 0 && slots[k] >= 0 && rd.s1[k] == 0) bcast = true;
                 }
                 // an operand broadcast over the rows is kept in registers for R rows; otherwise one-shot
-                rd.rows_per_cta = bcast ? 8 : 1;
+                // rows per CTA when an operand is broadcast over the rows.  Measured on cfg1 (B200): R = 2 / 4 / 8 / 16 /
+                // 32 -> 6.72 / 6.63 / 6.46 / 6.29 / 6.12 TB/s: the re-read of the broadcast operand is served by L2 and
+                // costs less than the parallelism lost to longer CTAs, so the default is one row (one-shot grid).
+                static const int rows_knob = [] { const char *e = getenv("RC_ROWS_PER_CTA"); int x = e ? atoi(e) : 1; return x >= 1 ? x : 1; }();
+                rd.rows_per_cta = bcast ? rows_knob : 1;
                 uint32_t chunks = (rd.n0 + EW_BLOCK * EW_UNROLL - 1) / (EW_BLOCK * EW_UNROLL);
                 rd.div_chunks = FastDiv(chunks);
                 int64_t groups = (rd.n1 + rd.rows_per_cta - 1) / rd.rows_per_cta;

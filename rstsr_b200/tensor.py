@@ -261,6 +261,21 @@ class Tensor:
             dev.op_mutc_refa_numb(op, raw, lc, self.raw, self.layout, other)
         return Tensor(raw, lc)
 
+    def consume(self, op: str, other: "Tensor", reverse: bool = False) -> "Tensor":
+        """`a op &b` with an OWNED `a` (reverse: `&b op a`): the result reuses `a`'s buffer when `b` broadcasts to
+        `a`'s own layout, through OpLConsume*API / OpRConsume*API (tensor/operators/op_binary_arithmetic.rs:280-354);
+        otherwise falls back to the allocating path."""
+        dev = self.device
+        if self.owned and op not in _FUNC_OPS and 0 not in [s for d, s in zip(self.shape, self.stride) if d > 1]:
+            try:
+                la_b, lb_b = broadcast_layout(self.layout, other.layout, dev.default_order())
+            except _ffi.RstsrCudaError:
+                la_b = None
+            if la_b is not None and la_b.ndim == self.ndim and la_b.same_as(self.layout):
+                dev.op_muta_refb(op, self.raw, la_b, other.raw, lb_b, reverse=reverse)
+                return Tensor(self.raw, la_b)
+        return other._binary(op, self) if reverse else self._binary(op, other)
+
     def _inplace(self, op: str, other) -> "Tensor":
         dev = self.device
         if isinstance(other, Tensor):

@@ -17,6 +17,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The C-ABI library is the product: build it (nvcc cross-compiles without a GPU) if a fresh checkout has none.
+    lib = os.path.join(ROOT, "rstsr_b200", "lib", "librstsr_cuda.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")

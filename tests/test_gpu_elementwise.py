@@ -379,3 +379,28 @@ def test_errors_mirror_the_reference(dev):
     with pytest.raises(rt.RstsrCudaError) as e:
         i.unary("sin")
     assert e.value.kind == "UnImplemented"
+
+
+def test_reference_consume_kats_on_device(dev):
+    """test_add_consume_row_major / test_sub_consume (op_binary_arithmetic.rs:1166-1317): an owned operand's
+    buffer is reused when the other operand broadcasts to its layout, otherwise a new one is allocated."""
+    lin = np.linspace
+    a, b = rt.asarray(lin(1, 5, 5), dev), rt.asarray(lin(2, 10, 5), dev)
+    c = a.consume("add", b)                                   # a + &b, same shape
+    assert c.raw.ptr == a.raw.ptr and c.to_numpy().tolist() == [3., 6., 9., 12., 15.]
+    a = rt.asarray(lin(1, 10, 10), dev).reshape([2, 5])
+    a.owned = True
+    c = a.consume("add", b)                                   # a + &b, b broadcasts to a
+    assert c.raw.ptr == a.raw.ptr
+    assert c.to_numpy().reshape(-1).tolist() == [3., 6., 9., 12., 15., 8., 11., 14., 17., 20.]
+    a = rt.asarray(lin(2, 10, 5), dev)
+    b2 = rt.asarray(lin(1, 10, 10), dev).reshape([2, 5])
+    c = a.consume("add", b2)                                  # a + &b, a would have to grow: new buffer
+    assert c.raw.ptr != a.raw.ptr
+    assert c.to_numpy().reshape(-1).tolist() == [3., 6., 9., 12., 15., 8., 11., 14., 17., 20.]
+    a, b = rt.asarray(lin(1, 5, 5), dev), rt.asarray(lin(2, 10, 5), dev)
+    c = b.consume("sub", a, reverse=True)                     # &a - b reuses b (OpRConsumeSubAPI: b = a - b)
+    assert c.raw.ptr == b.raw.ptr and c.to_numpy().tolist() == [-1., -2., -3., -4., -5.]
+    a, b = rt.asarray(lin(1, 5, 5), dev), rt.asarray(lin(2, 10, 5), dev)
+    c = a.consume("sub", b.view())                            # a - &b reuses a
+    assert c.raw.ptr == a.raw.ptr and c.to_numpy().tolist() == [-1., -2., -3., -4., -5.]
