@@ -327,6 +327,26 @@ int rc_reduce_axes_into(rc_device *dev, rc_redop op, rc_dtype dtype, const void 
                         const int64_t *axes, int naxes, void *out_dev, const rc_layout *lo);
 
 /* ------------------------------------------------------------------------------------------
+ * Binary reductions: two input streams folded in one pass.
+ *   rc_vecdot:       DeviceVecdotAPI::vecdot (rstsr-core/src/device_cpu_serial/linalg/vecdot.rs:4-29,
+ *                    rstsr-native-impl/src/cpu_serial/vecdot.rs:6-168): c[m] = sum_s a[m,s] * b[m,s];
+ *                    `axes_a` / `axes_b` pair the contracted axes (dim_split_axes order), the remaining
+ *                    axes of a and b must broadcast to lc's shape in the handle's default order.
+ *                    Errors as the reference: contracted shapes differ / c not broadcast from a, b
+ *                    -> RC_ERR_INVALID_LAYOUT.
+ *   rc_allclose_all: OpAllCloseAPI::allclose_all (rstsr-core/src/device_cpu_serial/reduction.rs:660-683)
+ *                    with isclose of rstsr-dtype-traits/src/isclose.rs:92-106 and TE = f64:
+ *                    all(|a-b| <= atol + rtol*|b| || (equal_nan && a,b NaN)); la, lb already broadcast to
+ *                    one shape (tensor level: rstsr-core/src/tensor/reduction.rs:324-351).  Zero size
+ *                    -> RC_ERR_INVALID_VALUE.  Synchronises the stream; *result = 0 / 1.
+ * Element types: f32, f64, i32, u32, i64, u64 (a, b and c share one dtype).
+ * ---------------------------------------------------------------------------------------- */
+int rc_vecdot(rc_device *dev, rc_dtype dtype, void *c, const rc_layout *lc, const void *a, const rc_layout *la,
+              const void *b, const rc_layout *lb, const int64_t *axes_a, const int64_t *axes_b, int naxes);
+int rc_allclose_all(rc_device *dev, rc_dtype dtype, const void *a, const rc_layout *la, const void *b,
+                    const rc_layout *lb, double rtol, double atol, int equal_nan, int *result);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU: one process (or handle) per GPU; shards are independent except for reductions whose
  * sharded axis is reduced.  The collective is NCCL all-reduce over NVLink.
  * ---------------------------------------------------------------------------------------- */

@@ -415,3 +415,81 @@ def reduce_ext(op: str, a, la: Layout, axes=None):
         dst = np.lib.stride_tricks.as_strided(out, shape=lo.shape, strides=tuple(s * item for s in lo.stride))
         dst[...] = res
     return out, lo
+
+
+# ---- binary reductions (test infrastructure, like everything in this package) ----
+def tensor_vecdot(a, la: Layout, b, lb: Layout, axes_a: Sequence[int], axes_b: Sequence[int], order: str = ROW_MAJOR):
+    """rt::vecdot (rstsr-core/src/tensor/linalg/vecdot.rs:177-243) + vecdot_naive_cpu_serial
+    (rstsr-native-impl/src/cpu_serial/vecdot.rs:6-168): -> (raw c, layout of c).  Sums in the element type
+    (integers wrap); the summation ORDER of the reference depends on its contiguity regime, so float parity is
+    a tolerance, not bit equality."""
+    axes_a = L.normalize_axes(axes_a, la.ndim)
+    axes_b = L.normalize_axes(axes_b, lb.ndim)
+    las, lam = L.dim_split_axes(la, axes_a)
+    lbs, lbm = L.dim_split_axes(lb, axes_b)
+    if tuple(las.shape) != tuple(lbs.shape):
+        raise LayoutError("InvalidLayout", "the dimensions of a and b along the contracted axis should be the same")
+    lam_b, lbm_b = L.broadcast_layout(lam, lbm, order)
+    lc = L.get_layout_for_binary_op(lam_b, lbm_b, order)
+    n = len(axes_a)
+    item_a, item_b = a.dtype.itemsize, b.dtype.itemsize
+    full_a = np.lib.stride_tricks.as_strided(a[la.offset:], shape=tuple(lam_b.shape) + tuple(las.shape),
+                                             strides=tuple(s * item_a for s in tuple(lam_b.stride) + tuple(las.stride)))
+    full_b = np.lib.stride_tricks.as_strided(b[lb.offset:], shape=tuple(lbm_b.shape) + tuple(lbs.shape),
+                                             strides=tuple(s * item_b for s in tuple(lbm_b.stride) + tuple(lbs.stride)))
+    red = tuple(range(len(lam_b.shape), len(lam_b.shape) + n))
+    with np.errstate(over="ignore"):
+        res = (full_a * full_b).sum(axis=red, dtype=a.dtype) if n else (full_a * full_b).astype(a.dtype)
+    out = np.zeros(max(L.bounds_index(lc)[1] if lc.size else 1, 1), dtype=a.dtype)
+    if lc.size:
+        dst = np.lib.stride_tricks.as_strided(out[lc.offset:], shape=lc.shape, strides=tuple(s * item_a for s in lc.stride))
+        dst[...] = res
+    return out, lc
+
+
+def isclose_scalar(a, b, rtol: float, atol: float, equal_nan: bool) -> bool:
+    """rstsr-dtype-traits/src/isclose.rs:92-106 with TE = f64 for two scalars of one numpy dtype."""
+    dt = np.asarray(a).dtype
+    with np.errstate(all="ignore"):
+        if dt.kind == "f":
+            diff = np.float64(np.abs(dt.type(a) - dt.type(b)))
+            abs_b = np.float64(np.abs(dt.type(b)))
+        elif dt.kind == "i":
+            ai, bi = int(a), int(b)
+            bits = dt.itemsize * 8
+            wrap = lambda v: ((v + (1 << (bits - 1))) % (1 << bits)) - (1 << (bits - 1))
+            diff = np.float64(wrap(ai - bi) if ai >= bi else wrap(bi - ai))
+            abs_b = np.float64(wrap(-bi) if bi < 0 else bi)
+        else:
+            ai, bi = int(a), int(b)
+            diff = np.float64(ai - bi if ai >= bi else bi - ai)
+            abs_b = np.float64(bi)
+        comp = bool(diff <= np.float64(atol) + np.float64(rtol) * abs_b)
+    nan_check = bool(equal_nan) and dt.kind == "f" and bool(np.isnan(a)) and bool(np.isnan(b))
+    return comp or nan_check
+
+
+def tensor_allclose(a, la: Layout, b, lb: Layout, rtol: float = 1.0e-5, atol: float = 1.0e-8, equal_nan: bool = False,
+                    order: str = ROW_MAJOR) -> bool:
+    """rt::allclose (rstsr-core/src/tensor/reduction.rs:324-351) -> allclose_all
+    (rstsr-core/src/device_cpu_serial/reduction.rs:660-683), vectorised restatement of isclose_scalar."""
+    la_b, lb_b = L.broadcast_layout(la, lb, order)
+    if la_b.size == 0 or lb_b.size == 0:
+        raise LayoutError("InvalidValue", "zero-size array is not supported for allclose")
+    va, vb = to_numpy(a, la_b), to_numpy(b, lb_b)
+    dt = a.dtype
+    with np.errstate(all="ignore"):
+        if dt.kind == "f":
+            diff = np.abs(va - vb).astype(np.float64)
+            abs_b = np.abs(vb).astype(np.float64)
+        elif dt.kind == "i":
+            ua, ub = va.astype(np.dtype(f"u{dt.itemsize}")), vb.astype(np.dtype(f"u{dt.itemsize}"))
+            diff = np.where(va >= vb, ua - ub, ub - ua).astype(dt).astype(np.float64)
+            abs_b = np.where(vb < 0, (np.zeros_like(ub) - ub).astype(dt), vb).astype(np.float64)
+        else:
+            diff = np.where(va >= vb, va - vb, vb - va).astype(np.float64)
+            abs_b = vb.astype(np.float64)
+        ok = diff <= np.float64(atol) + np.float64(rtol) * abs_b
+        if equal_nan and dt.kind == "f":
+            ok = ok | (np.isnan(va) & np.isnan(vb))
+    return bool(ok.all())

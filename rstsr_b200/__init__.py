@@ -8,10 +8,10 @@ from . import _ffi
 from ._ffi import RstsrCudaError
 from .device import (Comm, CudaRaw, DeviceCuda, Layout, broadcast_layout, layout_for_array_copy, layout_for_binary_op,
                      layout_for_reduce, layout_reshapeable)
-from .tensor import COL_MAJOR, ROW_MAJOR, Tensor, arange, asarray, empty, full, zeros
+from .tensor import COL_MAJOR, ROW_MAJOR, Tensor, allclose, arange, asarray, empty, full, vecdot, zeros
 
 _ffi.lib()  # fail loudly at import time if the extension is missing
 
 __all__ = ["DeviceCuda", "CudaRaw", "Layout", "Tensor", "Comm", "RstsrCudaError", "ROW_MAJOR", "COL_MAJOR", "asarray",
-           "arange", "zeros", "full", "empty", "broadcast_layout", "layout_for_array_copy", "layout_for_binary_op",
+           "arange", "zeros", "full", "empty", "vecdot", "allclose", "broadcast_layout", "layout_for_array_copy", "layout_for_binary_op",
            "layout_for_reduce", "layout_reshapeable"]

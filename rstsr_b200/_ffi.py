@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
 
 RC_MAX_NDIM = 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -114,6 +114,8 @@ SIGNATURES = {
     "rc_reduce_all_device": (c_int, [_P, c_int, c_int, _P, _L, _P]),
     "rc_reduce_axes": (c_int, [_P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, POINTER(_P), _L]),
     "rc_reduce_axes_into": (c_int, [_P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, _P, _L]),
+    "rc_vecdot": (c_int, [_P, c_int, _P, _L, _P, _L, _P, _L, POINTER(c_int64), POINTER(c_int64), c_int]),
+    "rc_allclose_all": (c_int, [_P, c_int, _P, _L, _P, _L, c_double, c_double, c_int, POINTER(c_int)]),
     "rc_comm_get_unique_id": (c_int, [POINTER(c_uint8)]),
     "rc_comm_init_rank": (c_int, [_P, c_int, c_int, POINTER(c_uint8), POINTER(_P)]),
     "rc_comm_destroy": (c_int, [_P]),

@@ -186,4 +186,71 @@ CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layo
     return c;
 }
 
+CanonRed canon_reduce_binary(const Layout &lam, const Layout &lbm, const Layout &lo, const Layout &las, const Layout &lbs,
+                             int64_t la_offset, int64_t lb_offset) {
+    CanonRed c;
+    c.binary = true;
+    c.base_in = la_offset;
+    c.base_in2 = lb_offset;
+    c.base_out = lo.offset;
+    RC_CHECK(lam.shape == lo.shape && lbm.shape == lo.shape, RC_ERR_INVALID_LAYOUT,
+             "kept axes of both inputs must be broadcast to the output shape");
+    RC_CHECK(las.shape == lbs.shape, RC_ERR_INVALID_LAYOUT, "reduced axes of both inputs must have one shape");
+    struct K { int64_t n, sa, sb, so; };
+    std::vector<K> ks;
+    for (int j = 0; j < lo.ndim(); ++j) {
+        if (lo.shape[j] == 0) { c.empty_out = true; return c; }
+        if (lo.shape[j] == 1) continue;
+        K k{lo.shape[j], lam.stride[j], lbm.stride[j], lo.stride[j]};
+        RC_CHECK(k.so != 0, RC_ERR_INVALID_LAYOUT, "output layout is broadcast (stride 0 on an axis of extent > 1)");
+        if (k.so < 0) {
+            c.base_in += (k.n - 1) * k.sa; k.sa = -k.sa;
+            c.base_in2 += (k.n - 1) * k.sb; k.sb = -k.sb;
+            c.base_out += (k.n - 1) * k.so; k.so = -k.so;
+        }
+        ks.push_back(k);
+    }
+    std::stable_sort(ks.begin(), ks.end(), [](const K &x, const K &y) { return x.so < y.so; });
+    for (const K &k : ks) {
+        if (!c.kshape.empty()) {
+            size_t p = c.kshape.size() - 1;
+            if (k.sa == c.kstride_in[p] * c.kshape[p] && k.sb == c.kstride_in2[p] * c.kshape[p] &&
+                k.so == c.kstride_out[p] * c.kshape[p]) {
+                c.kshape[p] *= k.n;
+                continue;
+            }
+        }
+        c.kshape.push_back(k.n);
+        c.kstride_in.push_back(k.sa);
+        c.kstride_in2.push_back(k.sb);
+        c.kstride_out.push_back(k.so);
+    }
+    struct R { int64_t n, sa, sb; };
+    std::vector<R> rs;
+    for (int i = 0; i < las.ndim(); ++i) {
+        if (las.shape[i] == 1) continue;
+        R r{las.shape[i], las.stride[i], lbs.stride[i]};
+        if (r.n > 0 && (r.sa < 0 || (r.sa == 0 && r.sb < 0))) {  // walk the pair backwards together
+            c.base_in += (r.n - 1) * r.sa; r.sa = -r.sa;
+            c.base_in2 += (r.n - 1) * r.sb; r.sb = -r.sb;
+        }
+        rs.push_back(r);
+    }
+    auto key = [](const R &r) { return r.sa != 0 ? r.sa : (r.sb < 0 ? -r.sb : r.sb); };
+    std::stable_sort(rs.begin(), rs.end(), [&](const R &x, const R &y) { return key(x) < key(y); });
+    for (const R &r : rs) {
+        if (!c.rshape.empty()) {
+            size_t p = c.rshape.size() - 1;
+            if (r.sa == c.rstride[p] * c.rshape[p] && r.sb == c.rstride2[p] * c.rshape[p]) {
+                c.rshape[p] *= r.n;
+                continue;
+            }
+        }
+        c.rshape.push_back(r.n);
+        c.rstride.push_back(r.sa);
+        c.rstride2.push_back(r.sb);
+    }
+    return c;
+}
+
 }  // namespace rc

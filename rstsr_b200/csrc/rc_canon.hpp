@@ -40,11 +40,20 @@ struct CanonRed {
     std::vector<int64_t> kshape, kstride_in, kstride_out;  // kept dims, dim 0 = fastest on the OUTPUT
     std::vector<int64_t> rshape, rstride;                  // reduced dims, dim 0 = smallest |stride|
     int64_t base_in = 0, base_out = 0;
+    // second input of a binary reduction (vecdot, allclose): same dims, its own strides
+    bool binary = false;
+    std::vector<int64_t> kstride_in2, rstride2;
+    int64_t base_in2 = 0;
     int64_t n_out() const { int64_t s = 1; for (auto d : kshape) s *= d; return s; }
     int64_t n_red() const { int64_t s = 1; for (auto d : rshape) s *= d; return s; }
 };
 // keep_order: the reduced dims keep the row-major order of `axes` (dim 0 = last axis given), are never flipped
 // or sorted and only merged when adjacent -- the flat reduced index then IS the row-major index arg* ops return.
 CanonRed canon_reduce(const Layout &la, const std::vector<int> &axes, const Layout &lo, bool keep_order = false);
+// Binary reduction out[k] = fold_r f(a[k, r], b[k, r]): kept views lam / lbm already broadcast to lo's shape,
+// reduced views las / lbs of one shape (offsets: la_offset / lb_offset, counted once).  The same flips, order and
+// merges are applied to both inputs, so the element pairing is preserved.
+CanonRed canon_reduce_binary(const Layout &lam, const Layout &lbm, const Layout &lo, const Layout &las, const Layout &lbs,
+                             int64_t la_offset, int64_t lb_offset);
 
 }  // namespace rc

@@ -50,7 +50,15 @@ struct RedDesc {
     int group;                  // rows kernel: threads per output
     int tcol;                   // cols kernel: threads along the kept axis
     int to_partial;             // write un-finalised states to the partial buffer
+    // binary reductions (vecdot, allclose): strides of the second input and the policy's run-time parameters
+    int64_t ks_in2[KMAXD], rs2[KMAXD];
+    double fp0, fp1;
+    int ip0;
 };
+
+// A policy with `static constexpr bool BINARY = true` reads two inputs and provides pre2(x, y, desc).
+template <class P, class = void> struct is_binary : std::false_type {};
+template <class P> struct is_binary<P, std::void_t<decltype(P::BINARY)>> : std::integral_constant<bool, P::BINARY> {};
 
 template <class T> using uns = typename std::make_unsigned<T>::type;
 
@@ -221,10 +229,13 @@ __device__ __forceinline__ S shfl_xor_state(S v, int m) {
 template <class P, int VEC, bool MULTI>
 __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_constant__ RedDesc d,
                                                                 const typename P::TI *__restrict__ in,
+                                                                const typename P::TI *__restrict__ in2,
                                                                 typename P::TO *__restrict__ out,
                                                                 typename P::S *__restrict__ partial) {
     using TI = typename P::TI;
     using S = typename P::S;
+    constexpr bool BIN = is_binary<P>::value;
+    constexpr int U = BIN ? RED_UNROLL / 2 : RED_UNROLL;  // same bytes in flight with two input streams
     __shared__ S warp_acc[RED_BLOCK / 32];
     const int G = d.group;
     const int tid = threadIdx.x;
@@ -232,9 +243,10 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
     const int64_t o = (int64_t)blockIdx.x * (RED_BLOCK / G) + g;
     const bool valid = o < d.n_out;
     int64_t off_out = 0;
-    const TI *src = in;
+    const TI *src = in, *src2 = in2;
     if (valid) {
         src += decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
+        if constexpr (BIN) src2 += decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_in2, d.big);
         off_out = decompose(o, 0, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
     }
     const int64_t begin = (int64_t)blockIdx.y * d.chunk;
@@ -247,30 +259,52 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
     for (int j = 0; j < VEC; ++j) acc[j] = P::init();
 
     const int64_t rs0 = d.rs[0];  // per item (already multiplied by VEC for packs)
+    const int64_t rs20 = BIN ? d.rs2[0] : 0;
     int64_t i = begin + t;
-    // full groups: RED_UNROLL independent loads in flight, no per-load predicate
-    for (; i + (int64_t)(RED_UNROLL - 1) * G < end; i += (int64_t)G * RED_UNROLL) {
-        Pack<TI, VEC> p[RED_UNROLL];
+    // full groups: U independent loads per input in flight, no per-load predicate
+    for (; i + (int64_t)(U - 1) * G < end; i += (int64_t)G * U) {
+        Pack<TI, VEC> p[U];
+        Pack<TI, VEC> q[BIN ? U : 1];
 #pragma unroll
-        for (int u = 0; u < RED_UNROLL; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t ii = i + (int64_t)u * G;
-            int64_t off;
-            if constexpr (MULTI) off = decompose(ii, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
-            else off = ii * rs0;
+            int64_t off, off2 = 0;
+            if constexpr (MULTI) {
+                off = decompose(ii, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+                if constexpr (BIN) off2 = decompose(ii, 0, d.nr, d.rshape, d.rdiv, d.rs2, d.big);
+            } else {
+                off = ii * rs0;
+                off2 = ii * rs20;
+            }
             p[u] = ld_stream<TI, VEC>(src + off);
+            if constexpr (BIN) q[u] = ld_stream<TI, VEC>(src2 + off2);
         }
 #pragma unroll
-        for (int u = 0; u < RED_UNROLL; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p[u].v[j], (i + (int64_t)u * G) * VEC + j));
+            for (int j = 0; j < VEC; ++j) {
+                if constexpr (BIN) acc[j] = P::comb(acc[j], P::pre2(p[u].v[j], q[u].v[j], d));
+                else acc[j] = P::comb(acc[j], P::pre(p[u].v[j], (i + (int64_t)u * G) * VEC + j));
+            }
     }
     for (; i < end; i += G) {
-        int64_t off;
-        if constexpr (MULTI) off = decompose(i, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
-        else off = i * rs0;
+        int64_t off, off2 = 0;
+        if constexpr (MULTI) {
+            off = decompose(i, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+            if constexpr (BIN) off2 = decompose(i, 0, d.nr, d.rshape, d.rdiv, d.rs2, d.big);
+        } else {
+            off = i * rs0;
+            off2 = i * rs20;
+        }
         Pack<TI, VEC> p = ld_stream<TI, VEC>(src + off);
+        if constexpr (BIN) {
+            Pack<TI, VEC> q = ld_stream<TI, VEC>(src2 + off2);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], i * VEC + j));
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre2(p.v[j], q.v[j], d));
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], i * VEC + j));
+        }
     }
     // fold the pack lanes, then the group, in a fixed order
     S v = acc[0];
@@ -300,11 +334,14 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
 template <class P, int VEC, bool MULTI>
 __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_constant__ RedDesc d,
                                                                 const typename P::TI *__restrict__ in,
+                                                                const typename P::TI *__restrict__ in2,
                                                                 typename P::TO *__restrict__ out,
                                                                 typename P::S *__restrict__ partial) {
     using TI = typename P::TI;
     using S = typename P::S;
     using TO = typename P::TO;
+    constexpr bool BIN = is_binary<P>::value;
+    constexpr int U = BIN ? RED_UNROLL / 2 : RED_UNROLL;
     extern __shared__ __align__(32) unsigned char red_smem[];
     S *sm = reinterpret_cast<S *>(red_smem);  // [RW][TC][VEC]
     const int TC = d.tcol, RW = RED_BLOCK / TC;
@@ -315,9 +352,10 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
     const int64_t col = (tile - kb * ntile0) * TC + tx;  // pack index along kept dim 0
     const bool valid = col < d.packs0;
     int64_t off_out = 0;
-    const TI *src = in;
+    const TI *src = in, *src2 = in2;
     if (valid) {
         src += col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
+        if constexpr (BIN) src2 += col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in2, d.big);
         off_out = col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
     }
     const int64_t begin = (int64_t)blockIdx.y * d.chunk;
@@ -330,29 +368,51 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
     for (int j = 0; j < VEC; ++j) acc[j] = P::init();
 
     const int64_t rs0 = d.rs[0];
+    const int64_t rs20 = BIN ? d.rs2[0] : 0;
     int64_t r = begin + ty;
-    for (; r + (int64_t)(RED_UNROLL - 1) * RW < end; r += (int64_t)RW * RED_UNROLL) {
-        Pack<TI, VEC> p[RED_UNROLL];
+    for (; r + (int64_t)(U - 1) * RW < end; r += (int64_t)RW * U) {
+        Pack<TI, VEC> p[U];
+        Pack<TI, VEC> q[BIN ? U : 1];
 #pragma unroll
-        for (int u = 0; u < RED_UNROLL; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t rr = r + (int64_t)u * RW;
-            int64_t off;
-            if constexpr (MULTI) off = decompose(rr, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
-            else off = rr * rs0;
+            int64_t off, off2 = 0;
+            if constexpr (MULTI) {
+                off = decompose(rr, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+                if constexpr (BIN) off2 = decompose(rr, 0, d.nr, d.rshape, d.rdiv, d.rs2, d.big);
+            } else {
+                off = rr * rs0;
+                off2 = rr * rs20;
+            }
             p[u] = ld_stream<TI, VEC>(src + off);
+            if constexpr (BIN) q[u] = ld_stream<TI, VEC>(src2 + off2);
         }
 #pragma unroll
-        for (int u = 0; u < RED_UNROLL; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p[u].v[j], r + (int64_t)u * RW));
+            for (int j = 0; j < VEC; ++j) {
+                if constexpr (BIN) acc[j] = P::comb(acc[j], P::pre2(p[u].v[j], q[u].v[j], d));
+                else acc[j] = P::comb(acc[j], P::pre(p[u].v[j], r + (int64_t)u * RW));
+            }
     }
     for (; r < end; r += RW) {
-        int64_t off;
-        if constexpr (MULTI) off = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
-        else off = r * rs0;
+        int64_t off, off2 = 0;
+        if constexpr (MULTI) {
+            off = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+            if constexpr (BIN) off2 = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs2, d.big);
+        } else {
+            off = r * rs0;
+            off2 = r * rs20;
+        }
         Pack<TI, VEC> p = ld_stream<TI, VEC>(src + off);
+        if constexpr (BIN) {
+            Pack<TI, VEC> q = ld_stream<TI, VEC>(src2 + off2);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], r));
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre2(p.v[j], q.v[j], d));
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], r));
+        }
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) sm[(ty * TC + tx) * VEC + j] = acc[j];
@@ -393,11 +453,13 @@ void fill_desc_dims(RedDesc &d, const CanonRed &c) {
         d.kshape[i] = c.kshape[i];
         d.ks_in[i] = c.kstride_in[i];
         d.ks_out[i] = c.kstride_out[i];
+        if (c.binary) d.ks_in2[i] = c.kstride_in2[i];
         if (c.kshape[i] >= (1ll << 31)) d.big = 1; else d.kdiv[i] = FastDiv((uint32_t)c.kshape[i]);
     }
     for (int i = 0; i < d.nr; ++i) {
         d.rshape[i] = c.rshape[i];
         d.rs[i] = c.rstride[i];
+        if (c.binary) d.rs2[i] = c.rstride2[i];
         if (c.rshape[i] >= (1ll << 31)) d.big = 1; else d.rdiv[i] = FastDiv((uint32_t)std::max<int64_t>(c.rshape[i], 1));
     }
 }
@@ -405,28 +467,28 @@ void fill_desc_dims(RedDesc &d, const CanonRed &c) {
 inline bool aligned_bytes(const void *p, size_t bytes) { return reinterpret_cast<uintptr_t>(p) % bytes == 0; }
 
 template <class P, int V>
-void launch_rows(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const typename P::TI *in, typename P::TO *out,
-                 typename P::S *partial) {
+void launch_rows(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const typename P::TI *in,
+                 const typename P::TI *in2, typename P::TO *out, typename P::S *partial) {
     int64_t gx = (d.n_out + (RED_BLOCK / d.group) - 1) / (RED_BLOCK / d.group);
     RC_CHECK(gx < (1ll << 31) && sy <= 65535, RC_ERR_UNIMPLEMENTED, "reduction grid too large");
     dim3 grid((unsigned)gx, (unsigned)sy);
     const bool multi = d.nr > 1;
     if constexpr (V > 1) {
         if (vec > 1) {
-            if (multi) reduce_rows_kernel<P, V, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
-            else reduce_rows_kernel<P, V, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
+            if (multi) reduce_rows_kernel<P, V, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out, partial);
+            else reduce_rows_kernel<P, V, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out, partial);
             after_launch(dev, "reduce_rows_kernel");
             return;
         }
     }
-    if (multi) reduce_rows_kernel<P, 1, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
-    else reduce_rows_kernel<P, 1, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, out, partial);
+    if (multi) reduce_rows_kernel<P, 1, true><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out, partial);
+    else reduce_rows_kernel<P, 1, false><<<grid, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out, partial);
     after_launch(dev, "reduce_rows_kernel");
 }
 
 template <class P, int V>
-void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const typename P::TI *in, typename P::TO *out,
-                 typename P::S *partial) {
+void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const typename P::TI *in,
+                 const typename P::TI *in2, typename P::TO *out, typename P::S *partial) {
     int64_t ntile0 = (d.packs0 + d.tcol - 1) / d.tcol;
     int64_t gx = ntile0 * d.n_out;
     RC_CHECK(gx < (1ll << 31) && sy <= 65535, RC_ERR_UNIMPLEMENTED, "reduction grid too large");
@@ -439,14 +501,14 @@ void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const ty
                 RC_CUDA(cudaFuncSetAttribute(reduce_cols_kernel<P, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 RC_CUDA(cudaFuncSetAttribute(reduce_cols_kernel<P, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             }
-            if (multi) reduce_cols_kernel<P, V, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
-            else reduce_cols_kernel<P, V, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
+            if (multi) reduce_cols_kernel<P, V, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, in2, out, partial);
+            else reduce_cols_kernel<P, V, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, in2, out, partial);
             after_launch(dev, "reduce_cols_kernel");
             return;
         }
     }
-    if (multi) reduce_cols_kernel<P, 1, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
-    else reduce_cols_kernel<P, 1, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, out, partial);
+    if (multi) reduce_cols_kernel<P, 1, true><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, in2, out, partial);
+    else reduce_cols_kernel<P, 1, false><<<grid, RED_BLOCK, smem, dev->stream>>>(d, in, in2, out, partial);
     after_launch(dev, "reduce_cols_kernel");
 }
 
@@ -461,13 +523,17 @@ int pow2_ceil(int64_t x) { int p = 1; while (p < x) p *= 2; return p; }
 
 // P: first-pass policy.  The second pass (over partial states) uses P::Second (P itself when pre is the identity).
 template <class P>
-void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, int64_t n_red_logical) {
+void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, int64_t n_red_logical,
+                  const void *b_v = nullptr, double fp0 = 0.0, double fp1 = 0.0, int ip0 = 0) {
     using TI = typename P::TI;
     using S = typename P::S;
     using TO = typename P::TO;
     using P2 = typename P::Second;
     if (c.empty_out) return;
+    constexpr bool BIN = is_binary<P>::value;
+    RC_CHECK(BIN == c.binary, RC_ERR_INVALID_VALUE, "internal: reduction arity mismatch");
     const TI *in = static_cast<const TI *>(a_v) + c.base_in;
+    const TI *in2 = BIN ? static_cast<const TI *>(b_v) + c.base_in2 : nullptr;
     TO *out = static_cast<TO *>(out_v) + c.base_out;
     constexpr int V = 32 / sizeof(TI);        // 256-bit packs of the element type
     constexpr bool SIMPLE = std::is_same<P2, P>::value;  // state == element, pre == identity
@@ -480,11 +546,12 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     std::memset(&d, 0, sizeof(d));
     fill_desc_dims(d, c);
     d.n_red = n_red_logical;
+    d.fp0 = fp0; d.fp1 = fp1; d.ip0 = ip0;
     d.n_out_total = n_out;
     if (n_out >= (1ll << 31)) d.big = 1;
 
-    const bool red_contig = d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] >= 8;
-    const bool kept_contig = d.nk >= 1 && d.ks_in[0] == 1 && d.ks_out[0] == 1 && d.kshape[0] >= 8;
+    const bool red_contig = d.nr >= 1 && d.rs[0] == 1 && (!BIN || d.rs2[0] == 1) && d.rshape[0] >= 8;
+    const bool kept_contig = d.nk >= 1 && d.ks_in[0] == 1 && (!BIN || d.ks_in2[0] == 1) && d.ks_out[0] == 1 && d.kshape[0] >= 8;
 
     auto second_pass_desc = [&](const RedDesc &first, int64_t Sx) {
         RedDesc e = first;
@@ -505,6 +572,11 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         bool vec_ok = V > 1 && d.kshape[0] % V == 0 && aligned_bytes(in, 32) && aligned_bytes(out, V * sizeof(TO));
         for (int i = 1; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0 && d.ks_out[i] % V == 0;
         for (int i = 0; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
+        if constexpr (BIN) {
+            vec_ok = vec_ok && aligned_bytes(in2, 32);
+            for (int i = 1; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in2[i] % V == 0;
+            for (int i = 0; i < d.nr && vec_ok; ++i) vec_ok = d.rs2[i] % V == 0;
+        }
         const int vec = vec_ok ? V : 1;
         d.packs0 = d.kshape[0] / vec;
         d.tcol = (int)std::min<int64_t>(tcol_max(), pow2_ceil(d.packs0));
@@ -520,12 +592,12 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         Sx = (n_red + d.chunk - 1) / d.chunk;
         if (Sx == 1) {
             d.to_partial = 0;
-            launch_cols<P, V>(dev, d, vec, 1, in, out, (S *)nullptr);
+            launch_cols<P, V>(dev, d, vec, 1, in, in2, out, (S *)nullptr);
             return;
         }
         S *partial = static_cast<S *>(workspace(dev, (size_t)Sx * n_out * sizeof(S)));
         d.to_partial = 1;
-        launch_cols<P, V>(dev, d, vec, Sx, in, out, partial);
+        launch_cols<P, V>(dev, d, vec, Sx, in, in2, out, partial);
         // second pass: fold partial[S][n_out] over S, same kept dims with contiguous input strides
         RedDesc e = second_pass_desc(d, Sx);
         constexpr int V2 = SIMPLE ? V : 1;
@@ -533,7 +605,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         const int v2 = vec2 ? V2 : 1;
         e.packs0 = e.kshape[0] / v2;
         e.tcol = (int)std::min<int64_t>(tcol_max(), pow2_ceil(e.packs0));
-        launch_cols<P2, V2>(dev, e, v2, 1, partial, out, (S *)nullptr);
+        launch_cols<P2, V2>(dev, e, v2, 1, partial, (const S *)nullptr, out, (S *)nullptr);
         return;
     }
 
@@ -541,17 +613,24 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     bool vec_ok = V > 1 && d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_bytes(in, 32);
     for (int i = 0; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0;
     for (int i = 1; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
+    if constexpr (BIN) {
+        vec_ok = vec_ok && d.rs2[0] == 1 && aligned_bytes(in2, 32);
+        for (int i = 0; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in2[i] % V == 0;
+        for (int i = 1; i < d.nr && vec_ok; ++i) vec_ok = d.rs2[i] % V == 0;
+    }
     const int vec = vec_ok ? V : 1;
     if (d.nr == 0) {  // nothing reduced (all reduced axes have extent 1): a strided copy through the monoid
         d.nr = 1;
         d.rshape[0] = 1;
         d.rs[0] = 0;
+        d.rs2[0] = 0;
         d.rdiv[0] = FastDiv(1);
     }
     if (vec > 1) {
         d.rshape[0] /= vec;
         d.rdiv[0] = FastDiv((uint32_t)std::max<int64_t>(d.rshape[0], 1));
         d.rs[0] = vec;
+        d.rs2[0] = vec;
     }
     d.n_out = n_out;
     d.n_items = n_red / vec;
@@ -569,16 +648,16 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     Sx = std::max<int64_t>(1, (d.n_items + d.chunk - 1) / d.chunk);
     if (Sx == 1) {
         d.to_partial = 0;
-        launch_rows<P, V>(dev, d, vec, 1, in, out, (S *)nullptr);
+        launch_rows<P, V>(dev, d, vec, 1, in, in2, out, (S *)nullptr);
         return;
     }
     S *partial = static_cast<S *>(workspace(dev, (size_t)Sx * n_out * sizeof(S)));
     d.to_partial = 1;
-    launch_rows<P, V>(dev, d, vec, Sx, in, out, partial);
+    launch_rows<P, V>(dev, d, vec, Sx, in, in2, out, partial);
     // second pass: out[o] = fold_s partial[s][o]
     RedDesc e = second_pass_desc(d, Sx);
     e.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, Sx / 2))));
-    launch_rows<P2, 1>(dev, e, 1, 1, partial, out, (S *)nullptr);
+    launch_rows<P2, 1>(dev, e, 1, 1, partial, (const S *)nullptr, out, (S *)nullptr);
 }
 
 // the five monoids of the hot path

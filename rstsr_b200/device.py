@@ -414,6 +414,31 @@ class DeviceCuda:
         check(_ffi.lib().rc_reduce_axes_into(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
                                              arr, len(axes), out.ptr, byref(lo.to_c())))
 
+    # ---- binary reductions ----
+    def vecdot(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, axes_a: Sequence[int],
+               axes_b: Sequence[int]):
+        """DeviceVecdotAPI::vecdot (rstsr-core/src/device_cpu_serial/linalg/vecdot.rs:16-28)."""
+        if not (a.dtype == b.dtype == c.dtype):
+            raise _ffi.RstsrCudaError(6, "vecdot: a, b and c must share one dtype")
+        if len(axes_a) != len(axes_b):
+            raise _ffi.RstsrCudaError(2, "axes_a and axes_b should have the same length")
+        n = len(axes_a)
+        aa = (ctypes.c_int64 * max(n, 1))(*[int(x) for x in axes_a])
+        ab = (ctypes.c_int64 * max(n, 1))(*[int(x) for x in axes_b])
+        check(_ffi.lib().rc_vecdot(self._handle, dtype_code(a.dtype), c.ptr, byref(lc.to_c()), a.ptr, byref(la.to_c()),
+                                   b.ptr, byref(lb.to_c()), aa, ab, n))
+
+    def allclose_all(self, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, rtol: float = 1.0e-5, atol: float = 1.0e-8,
+                     equal_nan: bool = False) -> bool:
+        """OpAllCloseAPI::allclose_all (rstsr-core/src/device_cpu_serial/reduction.rs:660-683); la / lb already
+        broadcast to one shape; defaults are IsCloseArgs::from(None) (rstsr-dtype-traits/src/isclose.rs:139-147)."""
+        if a.dtype != b.dtype:
+            raise _ffi.RstsrCudaError(6, "allclose_all: a and b must share one dtype")
+        r = ctypes.c_int(0)
+        check(_ffi.lib().rc_allclose_all(self._handle, dtype_code(a.dtype), a.ptr, byref(la.to_c()), b.ptr,
+                                         byref(lb.to_c()), float(rtol), float(atol), int(bool(equal_nan)), byref(r)))
+        return bool(r.value)
+
     # trait-named conveniences: sum_all / sum_axes / ... (operators/reduction.rs:26-32)
     def sum_all(self, a, la): return self.reduce_all("sum", a, la)
     def prod_all(self, a, la): return self.reduce_all("prod", a, la)

@@ -368,6 +368,60 @@ class Tensor:
     def count_nonzero_axes(self, axes): return self._reduce("count_nonzero", axes)
 
 
+# ---- binary reductions ----
+def _kept_layout(l: Layout, axes: Sequence[int]) -> Layout:
+    keep = [i for i in range(l.ndim) if i not in axes]
+    return Layout(tuple(l.shape[i] for i in keep), tuple(l.stride[i] for i in keep), l.offset)
+
+
+def vecdot(a: Tensor, b: Tensor, axis: Union[None, int, Tuple[Sequence[int], Sequence[int]]] = None) -> Tensor:
+    """rt::vecdot(a, b, axis) (rstsr-core/src/tensor/linalg/vecdot.rs:160-243): contracts `axis` (default -1, negative
+    counted from the end of EACH operand, non-negative must be < min(ndim)) or the axes pair (axes_a, axes_b); the
+    remaining axes broadcast in the device's default order; output layout by get_layout_for_binary_op."""
+    dev = a.device
+    if not dev.same_device(b.device):
+        raise _ffi.RstsrCudaError(5, "DeviceMismatch")
+    nmin = min(a.ndim, b.ndim)
+    if axis is None:
+        axis = -1
+    if isinstance(axis, (int, np.integer)):
+        axis = int(axis)
+        if axis < 0:
+            if not (-nmin <= axis <= -1):
+                raise _ffi.RstsrCudaError(2, "axis should be [-N, -1] where N is min(a.ndim, b.ndim)")
+            axes_a, axes_b = [axis + a.ndim], [axis + b.ndim]
+        else:
+            if not (0 <= axis < nmin):
+                raise _ffi.RstsrCudaError(2, "axis should be [0, N) where N is min(a.ndim, b.ndim)")
+            axes_a, axes_b = [axis], [axis]
+    else:
+        axes_a = [int(x) + a.ndim if int(x) < 0 else int(x) for x in axis[0]]
+        axes_b = [int(x) + b.ndim if int(x) < 0 else int(x) for x in axis[1]]
+        if len(axes_a) != len(axes_b):
+            raise _ffi.RstsrCudaError(2, "axes_a and axes_b should have the same length")
+        for ax, nd in ((axes_a, a.ndim), (axes_b, b.ndim)):
+            if any(not (0 <= x < nd) for x in ax) or len(set(ax)) != len(ax):
+                raise _ffi.RstsrCudaError(2, "axes out of bounds or repeated")
+    if [a.shape[i] for i in axes_a] != [b.shape[i] for i in axes_b]:
+        raise _ffi.RstsrCudaError(3, "the dimensions of a and b along the contracted axis should be the same")
+    order = dev.default_order()
+    lam_b, lbm_b = broadcast_layout(_kept_layout(a.layout, axes_a), _kept_layout(b.layout, axes_b), order)
+    lc = layout_for_binary_op(lam_b, lbm_b, order)
+    raw = dev.uninit_impl(a.dtype, max(lc.bounds_index()[1], 1))
+    dev.vecdot(raw, lc, a.raw, a.layout, b.raw, b.layout, axes_a, axes_b)
+    return Tensor(raw, lc)
+
+
+def allclose(a: Tensor, b: Tensor, rtol: float = 1.0e-5, atol: float = 1.0e-8, equal_nan: bool = False) -> bool:
+    """rt::allclose(a, b, args) (rstsr-core/src/tensor/reduction.rs:324-351): broadcast, then the device's
+    allclose_all.  Note the reference's isclose treats inf vs inf as NOT close (|inf - inf| is NaN)."""
+    dev = a.device
+    if not dev.same_device(b.device):
+        raise _ffi.RstsrCudaError(5, "DeviceMismatch")
+    la_b, lb_b = broadcast_layout(a.layout, b.layout, dev.default_order())
+    return dev.allclose_all(a.raw, la_b, b.raw, lb_b, rtol, atol, equal_nan)
+
+
 # ---- creation (rstsr-core/src/tensor/{asarray,creation}.rs) ----
 def asarray(data, device: DeviceCuda, layout: Optional[Layout] = None, dtype=None) -> Tensor:
     """asarray((vec, layout, &device)): upload a flat vector and view it through `layout`; a numpy array is
