@@ -347,6 +347,30 @@ int rc_allclose_all(rc_device *dev, rc_dtype dtype, const void *a, const rc_layo
                     const rc_layout *lb, double rtol, double atol, int equal_nan, int *result);
 
 /* ------------------------------------------------------------------------------------------
+ * Index-driven data movement.
+ *   rc_index_select: DeviceIndexSelectAPI::index_select (rstsr-core/src/device_cpu_serial/adv_indexing.rs:3-20,
+ *                    rstsr-native-impl/src/cpu_serial/adv_indexing.rs:3-90): c[.., i, ..] = a[.., indices[i], ..]
+ *                    along `axis`; `indices` is a HOST array (the trait takes &[usize]); lc.shape[axis] must
+ *                    equal n_indices (RC_ERR_INVALID_LAYOUT "Invalid index length."), an index outside
+ *                    0..la.shape[axis] is RC_ERR_INDEX "Index out of range.".
+ *   rc_pack_tri:     OpPackTriAPI::pack_tri (rstsr-core/src/device_cpu_serial/operators/op_tri.rs:4-28): `a` is the
+ *                    PACKED output (.., n(n+1)/2), `b` the full input (.., n, n); the triangle is walked row by
+ *                    row (rstsr-native-impl/src/cpu_serial/op_tri.rs:7-71).  Col-major handles see the axes
+ *                    reversed ((n, n, ..) / (n(n+1)/2, ..)) and the triangle flipped, as the reference does.
+ *   rc_unpack_tri:   OpUnpackTriAPI::unpack_tri (op_tri.rs:30-53): `a` is the FULL output, `b` the packed input;
+ *                    symm: Sy/He mirror, Ay/Ah mirror with a minus sign and a ZERO diagonal, N leaves the other
+ *                    triangle untouched (cpu_serial/op_tri.rs:152-446).  f32 / f64 (ComplexFloat in the reference).
+ * ---------------------------------------------------------------------------------------- */
+typedef enum rc_uplo { RC_UPLO_U = 0, RC_UPLO_L = 1 } rc_uplo;                                 /* FlagUpLo */
+typedef enum rc_symm { RC_SYMM_SY = 0, RC_SYMM_HE = 1, RC_SYMM_AY = 2, RC_SYMM_AH = 3, RC_SYMM_N = 4 } rc_symm; /* FlagSymm */
+int rc_index_select(rc_device *dev, rc_dtype dtype, void *c, const rc_layout *lc, const void *a, const rc_layout *la,
+                    int axis, const int64_t *indices, int64_t n_indices);
+int rc_pack_tri(rc_device *dev, rc_dtype dtype, void *a, const rc_layout *la, const void *b, const rc_layout *lb,
+                rc_uplo uplo);
+int rc_unpack_tri(rc_device *dev, rc_dtype dtype, void *a, const rc_layout *la, const void *b, const rc_layout *lb,
+                  rc_uplo uplo, rc_symm symm);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU: one process (or handle) per GPU; shards are independent except for reductions whose
  * sharded axis is reduced.  The collective is NCCL all-reduce over NVLink.
  * ---------------------------------------------------------------------------------------- */

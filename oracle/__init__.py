@@ -493,3 +493,90 @@ def tensor_allclose(a, la: Layout, b, lb: Layout, rtol: float = 1.0e-5, atol: fl
         if equal_nan and dt.kind == "f":
             ok = ok | (np.isnan(va) & np.isnan(vb))
     return bool(ok.all())
+
+
+# ---- index-driven movement (test infrastructure) ----
+def _wview(raw: np.ndarray, l: Layout) -> np.ndarray:
+    """writable strided view of `raw` through layout `l`"""
+    item = raw.dtype.itemsize
+    return np.lib.stride_tricks.as_strided(raw[l.offset:], shape=l.shape, strides=tuple(s * item for s in l.stride))
+
+
+def index_select(c, lc: Layout, a, la: Layout, axis: int, indices: Sequence[int]):
+    """index_select_cpu_serial (rstsr-native-impl/src/cpu_serial/adv_indexing.rs:3-90): c[.., i, ..] = a[.., idx[i], ..]."""
+    if lc.ndim != la.ndim:
+        raise LayoutError("InvalidLayout", "Input and output ndim should same.")
+    if lc.shape[axis] != len(indices):
+        raise LayoutError("InvalidLayout", "Invalid index length.")
+    if len(indices) and not (0 <= max(indices) < la.shape[axis]):
+        raise LayoutError("IndexError", "Index out of range.")
+    if lc.size == 0:
+        return
+    _wview(c, lc)[...] = np.take(to_numpy(a, la), np.asarray(indices, dtype=np.int64), axis=axis)
+
+
+def tensor_index_select(a, la: Layout, axis: int, indices: Sequence[int], order: str = ROW_MAJOR):
+    """index_select_f (rstsr-core/src/tensor/adv_indexing.rs:10-48) -> (raw, layout)."""
+    axis = axis + la.ndim if axis < 0 else axis
+    n = la.shape[axis]
+    idx = []
+    for i in indices:
+        i = n + i if i < 0 else i
+        if not 0 <= i < n:
+            raise LayoutError("IndexError", "Invalid index that exceeds shape length at axis")
+        idx.append(i)
+    shape = list(la.shape)
+    shape[axis] = len(idx)
+    lo = L.c_contig_layout(shape) if order == ROW_MAJOR else L.f_contig_layout(shape)
+    out = np.zeros(max(lo.size, 1), dtype=a.dtype)
+    index_select(out, lo, a, la, axis, idx)
+    return out, lo
+
+
+def _tri_pairs(n: int, uplo: str):
+    """(i, j) of the packed triangle in packing order: row by row (cpu_serial/op_tri.rs:25-71)."""
+    if uplo == "L":
+        pairs = [(i, j) for i in range(n) for j in range(i + 1)]
+    else:
+        pairs = [(i, j) for i in range(n) for j in range(i, n)]
+    I = np.array([p[0] for p in pairs], dtype=np.int64)
+    J = np.array([p[1] for p in pairs], dtype=np.int64)
+    return I, J
+
+
+def pack_tri(a, la: Layout, b, lb: Layout, uplo: str, order: str = ROW_MAJOR):
+    """OpPackTriAPI::pack_tri for DeviceCpuSerial (rstsr-core/src/device_cpu_serial/operators/op_tri.rs:8-27) +
+    pack_tri_cpu_serial (rstsr-native-impl/src/cpu_serial/op_tri.rs:73-148): a (packed) <- b (full)."""
+    if order != ROW_MAJOR:
+        la, lb = la.reverse_axes(), lb.reverse_axes()
+        uplo = "L" if uplo == "U" else "U"
+    n = lb.shape[-1]
+    if la.size == 0:
+        return
+    I, J = _tri_pairs(n, uplo)
+    _wview(a, la)[...] = to_numpy(b, lb)[..., I, J]
+
+
+def unpack_tri(a, la: Layout, b, lb: Layout, uplo: str, symm: str, order: str = ROW_MAJOR):
+    """OpUnpackTriAPI::unpack_tri (device_cpu_serial/operators/op_tri.rs:34-52) + unpack_tri_cpu_serial
+    (rstsr-native-impl/src/cpu_serial/op_tri.rs:152-522): a (full) <- b (packed).  symm N writes one triangle only."""
+    if order != ROW_MAJOR:
+        la, lb = la.reverse_axes(), lb.reverse_axes()
+        uplo = "L" if uplo == "U" else "U"
+    n = la.shape[-1]
+    if la.size == 0:
+        return
+    I, J = _tri_pairs(n, uplo)
+    va, vb = _wview(a, la), to_numpy(b, lb)
+    off = I != J
+    if symm in ("Sy", "He", "N"):
+        va[..., I, J] = vb
+        if symm != "N":
+            va[..., J[off], I[off]] = vb[..., off]
+    elif symm in ("Ay", "Ah"):
+        va[..., I[off], J[off]] = vb[..., off]
+        va[..., J[off], I[off]] = -vb[..., off]
+        d = np.arange(n)
+        va[..., d, d] = 0
+    else:
+        raise ValueError(symm)

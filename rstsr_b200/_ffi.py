@@ -34,6 +34,10 @@ REDOPS = dict(sum=0, prod=1, max=2, min=3, mean=4, var=5, std=6, l2_norm=7, argm
               count_nonzero=12)
 
 
+UPLO = {"U": 0, "L": 1}                              # rc_uplo / FlagUpLo
+SYMM = {"Sy": 0, "He": 1, "Ay": 2, "Ah": 3, "N": 4}  # rc_symm / FlagSymm
+
+
 class RstsrCudaError(RuntimeError):
     """Mirror of rstsr's `Error` (rstsr-common/src/error.rs:66-99): `.kind` is the RSTSRError variant name."""
 
@@ -116,6 +120,9 @@ SIGNATURES = {
     "rc_reduce_axes_into": (c_int, [_P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, _P, _L]),
     "rc_vecdot": (c_int, [_P, c_int, _P, _L, _P, _L, _P, _L, POINTER(c_int64), POINTER(c_int64), c_int]),
     "rc_allclose_all": (c_int, [_P, c_int, _P, _L, _P, _L, c_double, c_double, c_int, POINTER(c_int)]),
+    "rc_index_select": (c_int, [_P, c_int, _P, _L, _P, _L, c_int, POINTER(c_int64), c_int64]),
+    "rc_pack_tri": (c_int, [_P, c_int, _P, _L, _P, _L, c_int]),
+    "rc_unpack_tri": (c_int, [_P, c_int, _P, _L, _P, _L, c_int, c_int]),
     "rc_comm_get_unique_id": (c_int, [POINTER(c_uint8)]),
     "rc_comm_init_rank": (c_int, [_P, c_int, c_int, POINTER(c_uint8), POINTER(_P)]),
     "rc_comm_destroy": (c_int, [_P]),

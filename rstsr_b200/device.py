@@ -439,6 +439,31 @@ class DeviceCuda:
                                          byref(lb.to_c()), float(rtol), float(atol), int(bool(equal_nan)), byref(r)))
         return bool(r.value)
 
+    # ---- index-driven movement ----
+    def index_select(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, axis: int, indices: Sequence[int]):
+        """DeviceIndexSelectAPI::index_select (rstsr-core/src/device_cpu_serial/adv_indexing.rs:9-19); `indices`
+        are non-negative host integers (usize in the trait)."""
+        if a.dtype != c.dtype:
+            raise _ffi.RstsrCudaError(6, "index_select: a and c must share one dtype")
+        idx = np.ascontiguousarray(indices, dtype=np.int64).reshape(-1)
+        arr = idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+        check(_ffi.lib().rc_index_select(self._handle, dtype_code(a.dtype), c.ptr, byref(lc.to_c()), a.ptr,
+                                         byref(la.to_c()), int(axis), arr, idx.size))
+
+    def pack_tri(self, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, uplo: str):
+        """OpPackTriAPI::pack_tri (rstsr-core/src/device_cpu_serial/operators/op_tri.rs:8-27): a = packed out."""
+        if a.dtype != b.dtype:
+            raise _ffi.RstsrCudaError(6, "pack_tri: a and b must share one dtype")
+        check(_ffi.lib().rc_pack_tri(self._handle, dtype_code(a.dtype), a.ptr, byref(la.to_c()), b.ptr, byref(lb.to_c()),
+                                     _ffi.UPLO[uplo]))
+
+    def unpack_tri(self, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, uplo: str, symm: str):
+        """OpUnpackTriAPI::unpack_tri (rstsr-core/src/device_cpu_serial/operators/op_tri.rs:34-52): a = full out."""
+        if a.dtype != b.dtype:
+            raise _ffi.RstsrCudaError(6, "unpack_tri: a and b must share one dtype")
+        check(_ffi.lib().rc_unpack_tri(self._handle, dtype_code(a.dtype), a.ptr, byref(la.to_c()), b.ptr,
+                                       byref(lb.to_c()), _ffi.UPLO[uplo], _ffi.SYMM[symm]))
+
     # trait-named conveniences: sum_all / sum_axes / ... (operators/reduction.rs:26-32)
     def sum_all(self, a, la): return self.reduce_all("sum", a, la)
     def prod_all(self, a, la): return self.reduce_all("prod", a, la)

@@ -367,6 +367,95 @@ class Tensor:
     def any_axes(self, axes): return self._reduce("any", axes)
     def count_nonzero_axes(self, axes): return self._reduce("count_nonzero", axes)
 
+    # ---- index-driven movement ----
+    def index_select(self, axis: int, indices: Sequence[int]) -> "Tensor":
+        """tensor.index_select(axis, indices) (rstsr-core/src/tensor/adv_indexing.rs:10-48): negative indices count
+        from the end; the output is contiguous in the device's default order."""
+        dev = self.device
+        if not -self.ndim <= axis < self.ndim:
+            raise _ffi.RstsrCudaError(2, "axis out of bounds")
+        axis = axis + self.ndim if axis < 0 else axis
+        n = self.shape[axis]
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        idx = np.where(idx < 0, idx + n, idx)
+        if idx.size and (idx.min() < 0 or idx.max() >= n):
+            raise _ffi.RstsrCudaError(9, f"Invalid index that exceeds shape length at axis {axis}.")
+        shape = list(self.shape)
+        shape[axis] = int(idx.size)
+        lo = Layout.contig(shape, dev.default_order())
+        raw = dev.uninit_impl(self.dtype, max(lo.size, 1))
+        dev.index_select(raw, lo, self.raw, self.layout, axis, idx)
+        return Tensor(raw, lo)
+
+    def take(self, indices: Sequence[int], axis: int) -> "Tensor":
+        return self.index_select(axis, indices)
+
+    def _prefer(self, col: bool) -> bool:
+        """Layout::f_prefer / c_prefer (rstsr-common/src/layout/layoutbase.rs:89-142)."""
+        if self.ndim == 0 or self.layout.size == 0:
+            return True
+        dims = list(zip(self.stride, self.shape))
+        last = 0
+        for s, d in (dims if col else reversed(dims)):
+            if d != 1:
+                if s < last or (last == 0 and s != 1):
+                    return False
+                last = s
+            elif last == 0:
+                last = 1
+        return True
+
+    def _tri_out_layout(self, shape) -> Layout:
+        c, f = self._prefer(False), self._prefer(True)
+        if c and not f:
+            return Layout.contig(shape, ROW_MAJOR)
+        if f and not c:
+            return Layout.contig(shape, COL_MAJOR)
+        return Layout.contig(shape, self.device.default_order())
+
+    def pack_tri(self, uplo: str) -> "Tensor":
+        """tensor.pack_tri(uplo) (rstsr-core/src/tensor/operators/op_tri.rs:13-71): row-major devices pack the LAST two
+        axes into one of n(n+1)/2, col-major devices the FIRST two; the output follows the input's c/f preference."""
+        dev = self.device
+        if self.ndim < 2:
+            raise _ffi.RstsrCudaError(3, "pack_tri needs at least two axes")
+        if dev.default_order() == ROW_MAJOR:
+            n, m, rest = self.shape[-2], self.shape[-1], list(self.shape[:-2])
+            if n != m:
+                raise _ffi.RstsrCudaError(3, "Last two dimensions should be the same for pack_tri.")
+            shape = rest + [n * (n + 1) // 2]
+        else:
+            n, m, rest = self.shape[0], self.shape[1], list(self.shape[2:])
+            if n != m:
+                raise _ffi.RstsrCudaError(3, "First two dimensions should be the same for pack_tri.")
+            shape = [n * (n + 1) // 2] + rest
+        la = self._tri_out_layout(shape)
+        raw = dev.uninit_impl(self.dtype, max(la.bounds_index()[1], 1))
+        dev.pack_tri(raw, la, self.raw, self.layout, uplo)
+        return Tensor(raw, la)
+
+    def pack_tril(self): return self.pack_tri("L")
+    def pack_triu(self): return self.pack_tri("U")
+
+    def unpack_tri(self, uplo: str, symm: str) -> "Tensor":
+        """tensor.unpack_tri(uplo, symm) (rstsr-core/src/tensor/operators/op_tri.rs:106-163)."""
+        dev = self.device
+        if self.ndim < 1:
+            raise _ffi.RstsrCudaError(3, "unpack_tri needs at least one axis")
+        row = dev.default_order() == ROW_MAJOR
+        n_tp = self.shape[-1] if row else self.shape[0]
+        n = int(np.floor(np.sqrt(np.float64(2 * n_tp))))
+        if n * (n + 1) // 2 != n_tp:
+            raise _ffi.RstsrCudaError(3, ("Last" if row else "First") + " dimension should be triangular number for unpack_tri.")
+        shape = list(self.shape[:-1]) + [n, n] if row else [n, n] + list(self.shape[1:])
+        la = self._tri_out_layout(shape)
+        raw = dev.uninit_impl(self.dtype, max(la.bounds_index()[1], 1))
+        dev.unpack_tri(raw, la, self.raw, self.layout, uplo, symm)
+        return Tensor(raw, la)
+
+    def unpack_tril(self, symm: str): return self.unpack_tri("L", symm)
+    def unpack_triu(self, symm: str): return self.unpack_tri("U", symm)
+
 
 # ---- binary reductions ----
 def _kept_layout(l: Layout, axes: Sequence[int]) -> Layout:

@@ -1,0 +1,67 @@
+"""Scratch probe: achieved HBM bandwidth of index_select / pack_tri / unpack_tri next to torch (not product)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import rstsr_b200 as rt
+from rstsr_b200 import Layout
+
+torch.cuda.set_device(0)
+dev = rt.DeviceCuda(0, rt.ROW_MAJOR, stream=torch.cuda.current_stream().cuda_stream)
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def rep(name, nbytes, fn):
+    s = timeit(fn)
+    print(f"{name:62s} {nbytes / s / 1e9:8.1f} GB/s  {s * 1e6:8.1f} us", flush=True)
+
+
+n = 8192
+N = n * n
+a = torch.rand(N, dtype=torch.float64, device="cuda")
+c = torch.empty(N, dtype=torch.float64, device="cuda")
+ra, rc = dev.wrap(a.data_ptr(), N, np.float64), dev.wrap(c.data_ptr(), N, np.float64)
+full = Layout((n, n), (n, 1))
+rng = np.random.default_rng(0)
+idx = rng.integers(0, n, n).astype(np.int64)
+tidx = torch.from_numpy(idx).cuda()
+A = a.view(n, n)
+rep("index_select rows (8192,8192) f64, 8192 random rows", 2 * N * 8, lambda: dev.index_select(rc, full, ra, full, 0, idx))
+rep("index_select cols (8192,8192) f64, 8192 random cols", 2 * N * 8, lambda: dev.index_select(rc, full, ra, full, 1, idx))
+rep("torch.index_select rows", 2 * N * 8, lambda: torch.index_select(A, 0, tidx))
+rep("torch.index_select cols", 2 * N * 8, lambda: torch.index_select(A, 1, tidx))
+
+for batch, m in ((64, 1024), (4, 4096)):
+    tp = m * (m + 1) // 2
+    nf, npk = batch * m * m, batch * tp
+    f = torch.rand(nf, dtype=torch.float64, device="cuda")
+    p = torch.empty(npk, dtype=torch.float64, device="cuda")
+    rf, rp = dev.wrap(f.data_ptr(), nf, np.float64), dev.wrap(p.data_ptr(), npk, np.float64)
+    lf = Layout((batch, m, m), (m * m, m, 1))
+    lp = Layout((batch, tp), (tp, 1))
+    rep(f"pack_tril ({batch},{m},{m}) f64", 2 * npk * 8, lambda: dev.pack_tri(rp, lp, rf, lf, "L"))
+    rep(f"pack_triu ({batch},{m},{m}) f64", 2 * npk * 8, lambda: dev.pack_tri(rp, lp, rf, lf, "U"))
+    rep(f"unpack_tril Sy ({batch},{m},{m}) f64 [read tp + write n^2]", (npk + nf) * 8, lambda: dev.unpack_tri(rf, lf, rp, lp, "L", "Sy"))
+    rep(f"unpack_triu Ay ({batch},{m},{m}) f64", (npk + nf) * 8, lambda: dev.unpack_tri(rf, lf, rp, lp, "U", "Ay"))
+    rep(f"unpack_tril N ({batch},{m},{m}) f64 [read tp + write tp]", 2 * npk * 8, lambda: dev.unpack_tri(rf, lf, rp, lp, "L", "N"))
+    F = f.view(batch, m, m)
+    ti = torch.tril_indices(m, m, device="cuda")
+    rep("torch F[:, i, j] gather by tril_indices", 2 * npk * 8, lambda: F[:, ti[0], ti[1]])
+    del f, p

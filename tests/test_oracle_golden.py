@@ -350,3 +350,52 @@ def test_tensor_sum_cross_library():
         assert np.abs(oracle.to_numpy(out, lo) - a.reshape(4, 512, 512).sum(0)).max() < 1e-6
         out, lo = oracle.reduce_axes("sum", a, l, [-1, -2], device)
         assert np.abs(oracle.to_numpy(out, lo) - a.reshape(4, 512, 512).sum((-1, -2))).max() < 1e-6
+
+
+def test_vecdot_and_isclose_kats():
+    """rstsr-core/src/tensor/linalg/vecdot.rs:41-80 (doc tests) and rstsr-dtype-traits/src/isclose.rs:152-169."""
+    c, lc = oracle.tensor_vecdot(np.array([1, 2, 3]), L.c_contig_layout([3]), np.array([4, 5, 6]), L.c_contig_layout([3]), [-1], [-1])
+    assert lc.ndim == 0 and int(oracle.to_numpy(c, lc)) == 32
+    c, lc = oracle.tensor_vecdot(np.array([1, 2, 3, 4]), L.c_contig_layout([2, 2]), np.array([5, 6, 7, 8]),
+                                 L.c_contig_layout([2, 2]), [1], [1])
+    assert oracle.to_numpy(c, lc).tolist() == [17, 53]
+    a = np.array([0., 5., 0., 0., 0., 10., 0., 6., 8.])
+    c, lc = oracle.tensor_vecdot(a, L.c_contig_layout([3, 3]), np.array([0., 0.6, 0.8]), L.c_contig_layout([3]), [1], [0])
+    assert np.allclose(oracle.to_numpy(c, lc), [3., 8., 10.], rtol=1e-15)
+    f = np.float64
+    assert oracle.isclose_scalar(f(1.00001), f(1.00002), 1e-5, 1e-8, False) is True
+    assert oracle.isclose_scalar(f(1.00001), f(1.00002), 1e-6, 1e-9, False) is False
+    assert oracle.isclose_scalar(np.uint64(100), np.uint64(102), 1e-5, 1e-8, False) is False
+    l1 = L.c_contig_layout([1])
+    assert oracle.tensor_allclose(np.array([1.00001]), l1, np.array([1.00002]), l1) is True
+    assert oracle.tensor_allclose(np.array([100], dtype=np.uint64), l1, np.array([102], dtype=np.uint64), l1) is False
+
+
+def test_pack_unpack_tri_kats():
+    """rstsr-core/src/tensor/operators/op_tri.rs:187-228 (test_pack_tri), both default orders."""
+    a = np.arange(48.0)
+    lb, la = L.f_contig_layout([3, 4, 4]), L.f_contig_layout([3, 10])
+    packed = np.zeros(30)
+    oracle.pack_tri(packed, la, a, lb, "L", "row")
+    assert oracle.to_numpy(packed, la)[1].tolist() == [1., 4., 16., 7., 19., 31., 10., 22., 34., 46.]
+    full = np.zeros(48)
+    oracle.unpack_tri(full, lb, packed, la, "L", "Sy", "row")
+    assert oracle.to_numpy(full, lb)[0, 1].tolist() == [3., 15., 18., 21.]
+    lb, la = L.c_contig_layout([4, 4, 3]), L.c_contig_layout([10, 3])
+    packed = np.zeros(30)
+    oracle.pack_tri(packed, la, a, lb, "U", "col")
+    assert oracle.to_numpy(packed, la)[:, 1].tolist() == [1., 4., 16., 7., 19., 31., 10., 22., 34., 46.]
+    full = np.zeros(48)
+    oracle.unpack_tri(full, lb, packed, la, "U", "Sy", "col")
+    assert oracle.to_numpy(full, lb)[:, 1, 0].tolist() == [3., 15., 18., 21.]
+    # antisymmetric: zero diagonal, sign flip across it; N: only the stored triangle
+    p = np.arange(1.0, 7.0)
+    l6, l33 = L.c_contig_layout([6]), L.c_contig_layout([3, 3])
+    out = np.full(9, -1.0)
+    oracle.unpack_tri(out, l33, p, l6, "L", "Ay", "row")
+    assert out.reshape(3, 3).tolist() == [[0., -2., -4.], [2., 0., -5.], [4., 5., 0.]]
+    out = np.full(9, -1.0)
+    oracle.unpack_tri(out, l33, p, l6, "U", "N", "row")
+    assert out.reshape(3, 3).tolist() == [[1., 2., 3.], [-1., 4., 5.], [-1., -1., 6.]]
+    sel, ls = oracle.tensor_index_select(np.arange(12), L.c_contig_layout([3, 4]), 1, [3, -4, 1])
+    assert oracle.to_numpy(sel, ls).tolist() == [[3, 0, 1], [7, 4, 5], [11, 8, 9]]
