@@ -41,6 +41,10 @@ void run_reduce_ext_u64(rc_device *, rc_redop, const CanonRed &, const void *, v
 void run_reduce_ext_i32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 void run_reduce_ext_u32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 void run_reduce_bool(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_i8(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_u8(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_i16(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
+void run_reduce_u16(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 
 rc_dtype redop_out_dtype(rc_redop op, rc_dtype t) {
     switch (op) {
@@ -52,6 +56,13 @@ rc_dtype redop_out_dtype(rc_redop op, rc_dtype t) {
 
 void run_reduce(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out,
                 int64_t mean_count) {
+    switch (t) {  // narrow integers: base and "next" ops live in one TU per width
+        case RC_I8: run_reduce_i8(dev, op, cr, a, out, mean_count); return;
+        case RC_U8: run_reduce_u8(dev, op, cr, a, out, mean_count); return;
+        case RC_I16: run_reduce_i16(dev, op, cr, a, out, mean_count); return;
+        case RC_U16: run_reduce_u16(dev, op, cr, a, out, mean_count); return;
+        default: break;
+    }
     if (op >= RC_VAR) {  // the "next" reductions
         switch (t) {
             case RC_F64: run_reduce_ext_f64(dev, op, cr, a, out, mean_count); return;
