@@ -216,6 +216,12 @@ int rc_memcpy2d_h2d_async(rc_device *dev, void *dst_dev, size_t dst_pitch, const
  * `signaler` before it (cudaEventRecord + cudaStreamWaitEvent).  Handles of one ordinal are "the same device"
  * (rc_device_same_device); using several of them is how copies overlap kernels. */
 int rc_device_wait(rc_device *waiter, rc_device *signaler);
+/* DeviceChangeAPI between two DeviceCuda handles (rstsr-core/src/storage/conversion.rs:3-21; pattern
+ * crates-device/rstsr-openblas/src/conversion.rs:3-48): copy `nbytes` from `src` on src_dev to `dst` on dst_dev
+ * (same or different GPU; NVLink peer copy when available).  Stream-ordered on both handles: runs after the work
+ * already enqueued on src_dev, before anything enqueued later on either handle.  CPU <-> CUDA is
+ * rc_memcpy_h2d / rc_memcpy_d2h. */
+int rc_memcpy_peer(rc_device *dst_dev, void *dst_ptr, rc_device *src_dev, const void *src_ptr, size_t nbytes);
 int rc_get_index(rc_device *dev, rc_dtype dtype, const void *a, int64_t index, void *host_out);
 int rc_set_index(rc_device *dev, rc_dtype dtype, void *a, int64_t index, const void *host_value);
 /* pinned host staging buffers for outof_cpu_vec / to_cpu_vec */

@@ -81,6 +81,7 @@ SIGNATURES = {
     "rc_memcpy2d_d2h_async": (c_int, [_P, _P, c_size_t, _P, c_size_t, c_size_t, c_size_t]),
     "rc_memcpy2d_h2d_async": (c_int, [_P, _P, c_size_t, _P, c_size_t, c_size_t, c_size_t]),
     "rc_device_wait": (c_int, [_P, _P]),
+    "rc_memcpy_peer": (c_int, [_P, _P, _P, _P, c_size_t]),
     "rc_get_index": (c_int, [_P, c_int, _P, c_int64, _P]),
     "rc_set_index": (c_int, [_P, c_int, _P, c_int64, _P]),
     "rc_host_alloc": (c_int, [c_size_t, POINTER(_P)]),

@@ -357,6 +357,37 @@ int rc_device_wait(rc_device *waiter, rc_device *signaler) {
         if (e != cudaSuccess) raise(RC_ERR_DEVICE, std::string("rc_device_wait: ") + cudaGetErrorString(e));
     });
 }
+int rc_memcpy_peer(rc_device *dst_dev, void *dst, rc_device *src_dev, const void *src, size_t nbytes) {
+    return guard([&] {
+        RC_CHECK(dst_dev && src_dev, RC_ERR_INVALID_VALUE, "null device handle");
+        if (nbytes == 0) return;
+        check_ptr(dst, "dst"); check_ptr(src, "src");
+        // order: [work already on src stream] -> copy (on dst stream) -> [later work on either stream]
+        cudaEvent_t ready = nullptr, done = nullptr;
+        {
+            DeviceGuard gs(src_dev);
+            RC_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            cudaError_t e = cudaEventRecord(ready, src_dev->stream);
+            if (e != cudaSuccess) { cudaEventDestroy(ready); raise(RC_ERR_DEVICE, std::string("rc_memcpy_peer: ") + cudaGetErrorString(e)); }
+        }
+        cudaError_t e;
+        {
+            DeviceGuard gd(dst_dev);
+            e = cudaStreamWaitEvent(dst_dev->stream, ready, 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyPeerAsync(dst, dst_dev->ordinal, src, src_dev->ordinal, nbytes, dst_dev->stream);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(done, dst_dev->stream);
+        }
+        if (e == cudaSuccess && done) {
+            DeviceGuard gs(src_dev);
+            e = cudaStreamWaitEvent(src_dev->stream, done, 0);  // a later rc_free of `src` is ordered after the copy
+        }
+        cudaEventDestroy(ready);
+        if (done) cudaEventDestroy(done);
+        if (e != cudaSuccess) raise(RC_ERR_DEVICE, std::string("rc_memcpy_peer: ") + cudaGetErrorString(e));
+    });
+}
 int rc_memset(rc_device *dev, void *dst, int byte, size_t nbytes) {
     return guard([&] {
         DeviceGuard g(dev);

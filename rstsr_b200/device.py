@@ -189,6 +189,12 @@ class DeviceCuda:
         self._handle = h
         self.ordinal = ordinal
 
+    @staticmethod
+    def device_count() -> int:
+        n = ctypes.c_int(0)
+        check(_ffi.lib().rc_device_count(byref(n)))
+        return n.value
+
     def close(self):
         if self._handle:
             _ffi.lib().rc_device_destroy(self._handle)
@@ -290,6 +296,16 @@ class DeviceCuda:
     def wait(self, other: "DeviceCuda"):
         """Work enqueued on this handle from now on runs after what `other` has enqueued so far."""
         check(_ffi.lib().rc_device_wait(self._handle, other._handle))
+
+    def change_device(self, raw: CudaRaw, target: "DeviceCuda") -> CudaRaw:
+        """DeviceChangeAPI::change_device (rstsr-core/src/storage/conversion.rs:3-21) from this handle to `target`
+        (another stream of the same GPU, or another GPU: peer copy).  Returns new storage owned by `target`."""
+        if raw.device is not self and not raw.device.same_device(self):
+            raise _ffi.RstsrCudaError(5, "storage does not live on this device")
+        out = target.uninit_impl(raw.dtype, raw.len)
+        nbytes = raw.len * np.dtype(raw.dtype).itemsize
+        check(_ffi.lib().rc_memcpy_peer(target._handle, out.ptr, self._handle, raw.ptr, nbytes))
+        return out
 
     def h2d_async(self, raw: CudaRaw, host_ptr: int, nbytes: int, dst_byte_offset: int = 0):
         check(_ffi.lib().rc_memcpy_h2d_async(self._handle, raw.ptr + dst_byte_offset, host_ptr, nbytes))

@@ -186,6 +186,11 @@ class Tensor:
         dev.assign_uninit(raw, lc, self.raw, self.layout)
         return Tensor(raw, lc)
 
+    def to_device(self, target: DeviceCuda) -> "Tensor":
+        """tensor.into_device / to_device (DeviceChangeAPI, rstsr-core/src/storage/conversion.rs:3-21): the whole raw
+        buffer moves, the layout is kept as is."""
+        return Tensor(self.device.change_device(self.raw, target), self.layout)
+
     def astype(self, dtype) -> "Tensor":
         dev = self.device
         lc = layout_for_array_copy(self.layout, _ffi.ITER_K, dev.default_order())
@@ -509,6 +514,130 @@ def allclose(a: Tensor, b: Tensor, rtol: float = 1.0e-5, atol: float = 1.0e-8, e
         raise _ffi.RstsrCudaError(5, "DeviceMismatch")
     la_b, lb_b = broadcast_layout(a.layout, b.layout, dev.default_order())
     return dev.allclose_all(a.raw, la_b, b.raw, lb_b, rtol, atol, equal_nan)
+
+
+# ---- creation from tensors: compositions of OpAssignAPI (rstsr-core/src/tensor/creation_from_tensor.rs) ----
+def _check_axis(axis: int, ndim: int) -> int:
+    if not -ndim <= axis < ndim:
+        raise _ffi.RstsrCudaError(2, f"axis {axis} out of bounds for ndim {ndim}")
+    return axis + ndim if axis < 0 else axis
+
+
+def concat(tensors: Sequence[Tensor], axis: int = 0) -> Tensor:
+    """rt::concat((tensors, axis)) (creation_from_tensor.rs:321-386): a default-order contiguous result, one strided
+    `assign` per input into its slab."""
+    tensors = list(tensors)
+    if not tensors:
+        raise _ffi.RstsrCudaError(2, "concat requires at least one tensor.")
+    dev, ndim = tensors[0].device, tensors[0].ndim
+    if ndim == 0:
+        raise _ffi.RstsrCudaError(3, "All tensors must have ndim > 0 in concat.")
+    for t in tensors:
+        if t.ndim != ndim:
+            raise _ffi.RstsrCudaError(3, "All tensors must have the same ndim.")
+        if not t.device.same_device(dev):
+            raise _ffi.RstsrCudaError(5, "All tensors must be on the same device.")
+        if t.dtype != tensors[0].dtype:
+            raise _ffi.RstsrCudaError(6, "concat: all tensors must share one dtype")
+    axis = _check_axis(axis, ndim)
+    other = [d for i, d in enumerate(tensors[0].shape) if i != axis]
+    total = 0
+    for t in tensors:
+        if [d for i, d in enumerate(t.shape) if i != axis] != other:
+            raise _ffi.RstsrCudaError(3, "All tensors must have the same shape except for the concatenation axis.")
+        total += t.shape[axis]
+    shape = other[:axis] + [total] + other[axis:]
+    result = empty(shape, dev, dtype=tensors[0].dtype)
+    offset = 0
+    for t in tensors:
+        n = t.shape[axis]
+        key = tuple(slice(offset, offset + n) if i == axis else slice(None) for i in range(ndim))
+        slab = result[key]
+        dev.assign(result.raw, slab.layout, t.raw, t.layout)
+        offset += n
+    return result
+
+
+concatenate = concat
+
+
+def stack(tensors: Sequence[Tensor], axis: int = 0) -> Tensor:
+    """rt::stack((tensors, axis)) (creation_from_tensor.rs:643-684): expand_dims(axis) on every input, then concat."""
+    tensors = list(tensors)
+    if not tensors:
+        raise _ffi.RstsrCudaError(2, "stack requires at least one tensor.")
+    ndim = tensors[0].ndim
+    for t in tensors:
+        if t.shape != tensors[0].shape:
+            raise _ffi.RstsrCudaError(3, "All tensors must have the same shape.")
+    if not -(ndim + 1) <= axis <= ndim:
+        raise _ffi.RstsrCudaError(2, f"axis {axis} out of bounds for inserting into ndim {ndim}")
+    axis = axis + ndim + 1 if axis < 0 else axis
+    return concat([t.expand_dims(axis) for t in tensors], axis)
+
+
+def atleast_1d(t: Tensor) -> Tensor:
+    return t.expand_dims(0) if t.ndim == 0 else t.view()
+
+
+def atleast_2d(t: Tensor) -> Tensor:
+    if t.ndim == 0:
+        return t.expand_dims(0).expand_dims(1)
+    return t.expand_dims(0) if t.ndim == 1 else t.view()
+
+
+def hstack(tensors: Sequence[Tensor]) -> Tensor:
+    """creation_from_tensor.rs:505-526: atleast_1d, then concat along axis 0 (1-D inputs) or 1."""
+    if not len(tensors):
+        raise _ffi.RstsrCudaError(2, "hstack requires at least one tensor.")
+    ts = [atleast_1d(t) for t in tensors]
+    return concat(ts, 0 if ts[0].ndim == 1 else 1)
+
+
+def vstack(tensors: Sequence[Tensor]) -> Tensor:
+    """creation_from_tensor.rs:580-594: atleast_2d, then concat along axis 0."""
+    if not len(tensors):
+        raise _ffi.RstsrCudaError(2, "vstack requires at least one tensor.")
+    return concat([atleast_2d(t) for t in tensors], 0)
+
+
+def unstack(t: Tensor, axis: int = 0) -> list:
+    """creation_from_tensor.rs:783-812: views, one per index along `axis` (no copy)."""
+    if t.ndim == 0:
+        raise _ffi.RstsrCudaError(3, "unstack requires a tensor with ndim > 0.")
+    axis = _check_axis(axis, t.ndim)
+    return [t[tuple(i if k == axis else slice(None) for k in range(t.ndim))] for i in range(t.shape[axis])]
+
+
+def _diagonal_layout(l: Layout, offset: int) -> Layout:
+    """Layout::diagonal(offset, 0, 1) of a 2-D layout (rstsr-common/src/layout/layoutbase.rs:322-384)."""
+    d1, d2 = l.shape
+    t1, t2 = l.stride
+    if -d1 + 1 <= offset < 0:
+        off, n = l.offset + t1 * (-offset), min(d1 + offset, d2)
+    elif 0 <= offset < d1:
+        off, n = l.offset + t2 * offset, max(min(d2 - offset, d1), 0)
+    else:
+        off, n = l.offset, 0
+    return Layout((n,), (t1 + t2,), off)
+
+
+def diag(t: Tensor, offset: int = 0) -> Tensor:
+    """rt::diag((tensor, offset)) (creation_from_tensor.rs:48-82): 1-D -> matrix with the vector on diagonal `offset`
+    (zeros elsewhere); 2-D -> the diagonal as a new 1-D tensor."""
+    dev = t.device
+    if t.ndim == 1:
+        n = t.size + abs(offset)
+        result = full([n, n], 0, dev, dtype=t.dtype)
+        dev.assign(result.raw, _diagonal_layout(result.layout, offset), t.raw, t.layout)
+        return result
+    if t.ndim == 2:
+        ld = _diagonal_layout(t.layout, offset)
+        result = empty([ld.shape[0]], dev, dtype=t.dtype)
+        if ld.shape[0]:
+            dev.assign(result.raw, result.layout, t.raw, ld)
+        return result
+    raise _ffi.RstsrCudaError(3, "diag only support 1-D or 2-D tensor.")
 
 
 # ---- creation (rstsr-core/src/tensor/{asarray,creation}.rs) ----

@@ -207,3 +207,27 @@ def test_to_owned_uses_k_order(dev):
     o = a.to_owned()
     want = L.layout_for_array_copy(O(a.layout), "K")
     assert same(o.layout, want) and np.array_equal(o.to_numpy(), a.to_numpy())
+
+
+def test_change_device_between_handles(dev):
+    """DeviceChangeAPI between two DeviceCuda handles: another stream of the same GPU, and a second GPU if present."""
+    import rstsr_b200 as rt
+    rng = np.random.default_rng(seed_of("chdev"))
+    a = rng.standard_normal(1 << 20)
+    t = rt.asarray(a, dev).reshape([1024, 1024])[::2, ::-1]
+    other = rt.DeviceCuda(0, rt.COL_MAJOR)
+    targets = [other]
+    if rt.DeviceCuda.device_count() > 1:
+        targets.append(rt.DeviceCuda(1, rt.ROW_MAJOR))
+    try:
+        for tgt in targets:
+            moved = (t + 1.0).to_device(tgt)           # produced on dev's stream, consumed on the target's
+            assert moved.device is tgt and moved.shape == (512, 1024)
+            back = (moved * 2.0).to_device(dev)        # temporaries freed right after the copy is enqueued
+            want = (a.reshape(1024, 1024)[::2, ::-1] + 1.0) * 2.0
+            assert np.array_equal(back.to_numpy(), want)
+            v = t.to_device(tgt)
+            assert same(O(v.layout), O(t.layout)) and np.array_equal(v.to_numpy(), t.to_numpy())
+    finally:
+        for tgt in targets:
+            tgt.close()
