@@ -8,7 +8,7 @@
 //                    (rstsr-core/src/device_cpu_serial/operators/op_tri.rs:4-53,
 //                     rstsr-native-impl/src/cpu_serial/op_tri.rs:7-522)
 // All three are pure byte movement: HBM-bound, 2 x itemsize bytes per moved element.  Elements move as raw
-// 1/2/4/8/16-byte words; only the antisymmetric unpack (negation) is typed (f32 / f64, as ComplexFloat is in
+// 1/2/4/8/16/32-byte words; only the antisymmetric unpack (negation) is typed (f32 / f64, as ComplexFloat is in
 // the reference).
 #include <cmath>
 
@@ -299,7 +299,7 @@ bool make_rest(const Layout &lo_rest, const Layout &li_rest, RestDesc *d, int64_
 int promote_word(RestDesc *r, int e, const std::vector<int64_t *> &other_strides, const void *po, const void *pi,
                  int64_t *base_out, int64_t *base_in) {
     if (r->nd == 0 || r->s_out[0] != 1 || r->s_in[0] != 1) return e;
-    for (int w = 16; w > e; w /= 2) {
+    for (int w = 32; w > e; w /= 2) {
         const int f = w / e;
         bool ok = r->shape[0] % f == 0 && *base_out % f == 0 && *base_in % f == 0 &&
                   reinterpret_cast<uintptr_t>(po) % w == 0 && reinterpret_cast<uintptr_t>(pi) % w == 0;
@@ -365,6 +365,7 @@ void launch_unpack(rc_device *dev, const TriMoveDesc &d, void *f, int64_t bf, co
 }
 
 struct alignas(16) Word16 { uint64_t a, b; };
+struct alignas(32) Word32 { uint64_t a, b, c, d; };
 
 // row-major view of the problem: the reference runs col-major devices on reversed axes with the other triangle
 // (device_cpu_serial/operators/op_tri.rs:17-26)
@@ -427,7 +428,8 @@ int rc_index_select(rc_device *dev, rc_dtype t, void *c, const rc_layout *lc_, c
                 case 2: launch_select<uint16_t>(dev, d, c, bc, a, ba, idx_dev); break;
                 case 4: launch_select<uint32_t>(dev, d, c, bc, a, ba, idx_dev); break;
                 case 8: launch_select<uint64_t>(dev, d, c, bc, a, ba, idx_dev); break;
-                default: launch_select<Word16>(dev, d, c, bc, a, ba, idx_dev); break;
+                case 16: launch_select<Word16>(dev, d, c, bc, a, ba, idx_dev); break;
+                default: launch_select<Word32>(dev, d, c, bc, a, ba, idx_dev); break;
             }
         } catch (...) {
             cudaFreeAsync(idx_dev, dev->stream);
@@ -485,7 +487,8 @@ int rc_pack_tri(rc_device *dev, rc_dtype t, void *a, const rc_layout *la_, const
             case 2: launch_pack<uint16_t>(dev, d, a, bp, b, bf); break;
             case 4: launch_pack<uint32_t>(dev, d, a, bp, b, bf); break;
             case 8: launch_pack<uint64_t>(dev, d, a, bp, b, bf); break;
-            default: launch_pack<Word16>(dev, d, a, bp, b, bf); break;
+            case 16: launch_pack<Word16>(dev, d, a, bp, b, bf); break;
+            default: launch_pack<Word32>(dev, d, a, bp, b, bf); break;
         }
     });
 }
