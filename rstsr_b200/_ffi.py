@@ -29,7 +29,8 @@ BINOPS = dict(add=0, sub=1, mul=2, div=3, rem=4, bitor=5, bitand=6, bitxor=7, sh
 UNOPS = dict(neg=0, not_=1, abs=2, square=3, sign=4, sqrt=5, exp=6, expm1=7, log=8, log2=9, log10=10, sin=11, cos=12,
              tan=13, asin=14, acos=15, atan=16, sinh=17, cosh=18, tanh=19, asinh=20, acosh=21, atanh=22, floor=23,
              ceil=24, round=25, trunc=26, reciprocal=27, conj=28, real=29, imag=30, isnan=48, isinf=49, isfinite=50,
-             signbit=51)
+             signbit=51,
+             inv=27)  # OpInvAPI and OpReciprocalAPI are both b.recip() (auto_impl/op_binary_common.rs:25,29)
 REDOPS = dict(sum=0, prod=1, max=2, min=3, mean=4, var=5, std=6, l2_norm=7, argmin=8, argmax=9, all=10, any=11,
               count_nonzero=12)
 

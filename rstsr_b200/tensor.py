@@ -372,6 +372,14 @@ class Tensor:
     def any_axes(self, axes): return self._reduce("any", axes)
     def count_nonzero_axes(self, axes): return self._reduce("count_nonzero", axes)
 
+    def unraveled_argmin_all(self) -> Tuple[int, ...]:
+        """OpUnraveledArgMinAPI::unraveled_argmin_all (operators/reduction.rs:38-55): the multi-index of argmin_all's
+        row-major flat index.  (The `_axes` variant returns a tensor of index VECTORS -- not a POD element type.)"""
+        return tuple(int(i) for i in np.unravel_index(int(self.argmin_all()), self.shape))
+
+    def unraveled_argmax_all(self) -> Tuple[int, ...]:
+        return tuple(int(i) for i in np.unravel_index(int(self.argmax_all()), self.shape))
+
     # ---- index-driven movement ----
     def index_select(self, axis: int, indices: Sequence[int]) -> "Tensor":
         """tensor.index_select(axis, indices) (rstsr-core/src/tensor/adv_indexing.rs:10-48): negative indices count

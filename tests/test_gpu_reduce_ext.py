@@ -143,3 +143,16 @@ def test_large_shapes_hit_vector_and_split_paths(dev, shape, axes):
     assert np.array_equal(t.argmin_axes(axes).to_numpy(), flat.argmin(-1).astype(np.uint64))
     assert np.array_equal((t.binary("gt", 0.5)).count_nonzero_axes(axes).to_numpy(), (an > 0.5).sum(axis=ax).astype(np.uint64))
     assert t.argmax_all() == int(an.argmax()) and t.argmin_all() == int(an.argmin())
+
+
+def test_unraveled_arg_all(dev, dev_col):
+    """unraveled_argmin_all / unraveled_argmax_all: multi-index of the first extreme element in row-major order"""
+    rng = np.random.default_rng(seed_of("unravel"))
+    v = rng.integers(-50, 50, (5, 6, 7)).astype(np.int64)
+    for d in (dev, dev_col):
+        t = rt.asarray(v, d)
+        assert t.unraveled_argmin_all() == tuple(int(i) for i in np.unravel_index(np.argmin(v), v.shape))
+        assert t.unraveled_argmax_all() == tuple(int(i) for i in np.unravel_index(np.argmax(v), v.shape))
+        tt = t.transpose([2, 0, 1])[::-1]
+        vv = v.transpose(2, 0, 1)[::-1]
+        assert tt.unraveled_argmax_all() == tuple(int(i) for i in np.unravel_index(np.argmax(vv), vv.shape))
