@@ -28,6 +28,19 @@ void *workspace(rc_device *d, size_t nbytes) {
     return p;
 }
 
+void *scalar_slot(rc_device *d, void **host) {
+    if (!d->slot_host) {
+        void *h = nullptr, *p = nullptr;
+        RC_CUDA(cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        cudaError_t e = cudaHostGetDevicePointer(&p, h, 0);
+        if (e != cudaSuccess) { cudaFreeHost(h); raise(RC_ERR_DEVICE, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e)); }
+        d->slot_host = h;
+        d->slot_dev = p;
+    }
+    *host = d->slot_host;
+    return d->slot_dev;
+}
+
 void run_reduce_f64(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 void run_reduce_f32(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 void run_reduce_i64(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
@@ -234,6 +247,7 @@ int rc_device_destroy(rc_device *dev) {
         cudaSetDevice(dev->ordinal);
         cudaStreamSynchronize(dev->stream);
         if (dev->ws) cudaFree(dev->ws);
+        if (dev->slot_host) cudaFreeHost(dev->slot_host);
         if (dev->own_stream) cudaStreamDestroy(dev->stream);
         delete dev;
     });
@@ -698,19 +712,13 @@ int rc_reduce_all(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const 
         Layout la = from_c(la_);
         check_ptr(host_out, "host_out");
         if (la.size() != 0) check_ptr(a, "a");
-        void *slot = nullptr;
-        cudaError_t e = cudaMallocAsync(&slot, 16, dev->stream);
-        if (e != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
-        try {
-            Layout lo;
-            reduce_into(dev, op, t, a, la, all_axes(la.ndim()), slot, lo);
-            RC_CUDA(cudaMemcpyAsync(host_out, slot, dtype_size(redop_out_dtype(op, t)), cudaMemcpyDeviceToHost, dev->stream));
-            RC_CUDA(cudaStreamSynchronize(dev->stream));
-        } catch (...) {
-            cudaFreeAsync(slot, dev->stream);
-            throw;
-        }
-        RC_CUDA(cudaFreeAsync(slot, dev->stream));
+        std::lock_guard<std::mutex> slot_lock(dev->slot_mu);
+        void *host = nullptr;
+        void *slot = scalar_slot(dev, &host);
+        Layout lo;
+        reduce_into(dev, op, t, a, la, all_axes(la.ndim()), slot, lo);
+        RC_CUDA(cudaStreamSynchronize(dev->stream));
+        std::memcpy(host_out, host, dtype_size(redop_out_dtype(op, t)));
     });
 }
 

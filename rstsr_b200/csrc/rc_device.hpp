@@ -17,6 +17,12 @@ struct rc_device {
     std::mutex ws_mu;
     void *ws = nullptr;
     size_t ws_bytes = 0;
+    // 64-byte pinned + mapped host slot: kernels of `*_all` reductions write their scalar straight into host
+    // memory, so the call costs launch + stream sync (no allocation, no D2H copy).  Held under slot_mu from the
+    // launch until the host has read the value.
+    std::mutex slot_mu;
+    void *slot_host = nullptr;
+    void *slot_dev = nullptr;
 };
 
 namespace rc {
@@ -43,5 +49,6 @@ inline void after_launch(rc_device *d, const char *what) {
 }
 
 void *workspace(rc_device *d, size_t nbytes);  // stream-ordered scratch, valid until the next call
+void *scalar_slot(rc_device *d, void **host);  // device view of the handle's mapped host slot (caller holds slot_mu)
 
 }  // namespace rc

@@ -121,22 +121,15 @@ int rc_allclose_all(rc_device *dev, rc_dtype t, const void *a, const rc_layout *
         check_dev_ptr(a, "a"); check_dev_ptr(b, "b");
         Layout kept;  // 0-d: everything is reduced
         CanonRed cr = canon_reduce_binary(kept, kept, kept, la, lb, la.offset, lb.offset);
-        void *slot = nullptr;
-        cudaError_t e = cudaMallocAsync(&slot, 16, dev->stream);
-        if (e != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
-        uint8_t host = 0;
-        try {
-            {
-                std::lock_guard<std::mutex> lock(dev->ws_mu);
-                dispatch<PClose>(dev, t, cr, a, b, slot, la.size(), rtol, atol, equal_nan ? 1 : 0);
-            }
-            RC_CUDA(cudaMemcpyAsync(&host, slot, 1, cudaMemcpyDeviceToHost, dev->stream));
-            RC_CUDA(cudaStreamSynchronize(dev->stream));
-        } catch (...) {
-            cudaFreeAsync(slot, dev->stream);
-            throw;
+        std::lock_guard<std::mutex> slot_lock(dev->slot_mu);
+        void *host_slot = nullptr;
+        void *slot = scalar_slot(dev, &host_slot);
+        {
+            std::lock_guard<std::mutex> lock(dev->ws_mu);
+            dispatch<PClose>(dev, t, cr, a, b, slot, la.size(), rtol, atol, equal_nan ? 1 : 0);
         }
-        RC_CUDA(cudaFreeAsync(slot, dev->stream));
+        RC_CUDA(cudaStreamSynchronize(dev->stream));
+        const uint8_t host = *static_cast<const volatile uint8_t *>(host_slot);
         *result = host ? 1 : 0;
     });
 }
