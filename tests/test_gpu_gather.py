@@ -90,6 +90,17 @@ def test_index_select_large_rows(dev):
     t = rt.asarray(a, dev)
     assert np.array_equal(t.index_select(0, idx).to_numpy(), a[idx])
     assert np.array_equal(t.index_select(1, idx[:100]).to_numpy(), a[:, idx[:100]])
+    # gather along the contiguous axis with most of each row wanted: rows staged in shared memory
+    assert np.array_equal(t.index_select(1, idx).to_numpy(), a[:, idx])
+    assert np.array_equal(t[::2, 7:4000].index_select(1, idx[:3000] % 3993).to_numpy(), a[::2, 7:4000][:, idx[:3000] % 3993])
+    for dt in (np.float32, np.int16, np.uint8):
+        b = (a * 100).astype(dt)
+        assert np.array_equal(rt.asarray(b, dev).index_select(-1, idx).to_numpy(), b[:, idx])
+    out = rt.full([4096, 8192], -3.0, dev)
+    oc = out[:, ::2]
+    dev.index_select(oc.raw, oc.layout, t.raw, t.layout, 1, idx)
+    o = out.to_numpy()
+    assert np.array_equal(o[:, ::2], a[:, idx]) and np.all(o[:, 1::2] == -3.0)
     f = rt.asarray(a.astype(np.float32), dev)
     assert np.array_equal(f[1:, 1:].index_select(0, idx[:500] % 4095).to_numpy(), a.astype(np.float32)[1:, 1:][idx[:500] % 4095])
 
