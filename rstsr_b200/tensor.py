@@ -178,6 +178,14 @@ class Tensor:
         order = self.device.default_order() if order is None else order
         return self.to_layout(Layout.contig(self.shape, order))
 
+    def to_prefer(self, order: Optional[int] = None) -> "Tensor":
+        """to_prefer / change_prefer_f (manipulation/to_contig.rs:229-243): a view if the layout already is c- (f-)
+        preferred, otherwise the contiguous copy."""
+        order = self.device.default_order() if order is None else order
+        if self._prefer(order == COL_MAJOR):
+            return self.view()
+        return self.to_contig(order)
+
     def to_owned(self) -> "Tensor":
         """asarray((&t, K)) (rstsr-core/src/tensor/asarray.rs:321-341): same-shape copy into a K-order layout."""
         dev = self.device
