@@ -686,6 +686,25 @@ def full(shape: Sequence[int], value, device: DeviceCuda, dtype=np.float64) -> T
     return Tensor(device.full_impl(dtype, max(l.size, 1), value), l)
 
 
+def ones(shape: Sequence[int], device: DeviceCuda, dtype=np.float64) -> Tensor:
+    l = Layout.contig(shape, device.default_order())
+    return Tensor(device.ones_impl(dtype, max(l.size, 1)), l)
+
+
+def eye(n_rows: int, device: DeviceCuda, n_cols: Optional[int] = None, k: int = 0, order: Optional[int] = None,
+        dtype=np.float64) -> Tensor:
+    """rt::eye((n_rows, n_cols, k, order, &device)) (rstsr-core/src/tensor/creation.rs:409-427): zeros_impl, then `fill`
+    of the k-th diagonal view with one.  As in the reference, ColMajor builds the [n_cols, n_rows].f() layout."""
+    n_cols = n_rows if n_cols is None else n_cols
+    order = device.default_order() if order is None else order
+    layout = Layout.contig([n_rows, n_cols], ROW_MAJOR) if order == ROW_MAJOR else Layout.contig([n_cols, n_rows], COL_MAJOR)
+    raw = device.zeros_impl(dtype, max(layout.size, 1))
+    ld = _diagonal_layout(layout, k)
+    if ld.shape[0]:
+        device.fill(raw, ld, 1)
+    return Tensor(raw, layout)
+
+
 def empty(shape: Sequence[int], device: DeviceCuda, dtype=np.float64) -> Tensor:
     l = Layout.contig(shape, device.default_order())
     return Tensor(device.uninit_impl(dtype, max(l.size, 1)), l)

@@ -187,3 +187,26 @@ def test_is_nan_is_finite_is_inf(device):
     assert a.unary("isnan").to_vec().tolist() == [False, True, False, False]
     assert a.unary("isfinite").to_vec().tolist() == [True, False, False, False]
     assert a.unary("isinf").to_vec().tolist() == [False, False, True, True]
+
+
+# ---- creation/test_eye.rs, test_ones.rs, test_zeros.rs, test_full.rs ----
+def test_eye_basic_and_rect_offset(device, dev_col):
+    expected = T([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], device, np.int32)
+    assert_equal(rt.eye(4, device, dtype=np.int32), expected)
+    assert_equal(rt.eye(4, device, dtype=np.float32), expected.astype(np.float32))
+    assert_equal(rt.eye(3, device, 4, 1, dtype=np.int32), T([[0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], device, np.int32))
+    for n, m, k in ((3, 5, 0), (5, 3, -1), (4, 4, 2), (4, 4, -3), (2, 6, 4)):
+        # Layout::diagonal only accepts offsets in (-rows, rows) (layoutbase.rs:352-363): beyond that the reference's
+        # eye stays all-zero even where NumPy's would not (wide matrices, k >= rows)
+        want = np.eye(n, m, k) if -n < k < n else np.zeros((n, m))
+        assert np.array_equal(rt.eye(n, device, m, k).to_numpy(), want)
+    # ColMajor builds [n_cols, n_rows].f() (tensor/creation.rs:418-421)
+    e = rt.eye(3, dev_col, 4, 0)
+    assert e.shape == (4, 3) and e.layout.f_contig() and np.array_equal(e.to_numpy(), np.eye(4, 3))
+
+
+def test_ones_zeros_full(device):
+    assert np.array_equal(rt.ones([2, 3], device, dtype=np.int32).to_numpy(), np.ones((2, 3), np.int32))
+    assert np.array_equal(rt.zeros([2, 3], device).to_numpy(), np.zeros((2, 3)))
+    assert np.array_equal(rt.full([2, 2], 7.5, device).to_numpy(), np.full((2, 2), 7.5))
+    assert rt.ones([0, 3], device).shape == (0, 3)
