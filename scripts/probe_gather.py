@@ -65,3 +65,16 @@ for batch, m in ((64, 1024), (4, 4096)):
     ti = torch.tril_indices(m, m, device="cuda")
     rep("torch F[:, i, j] gather by tril_indices", 2 * npk * 8, lambda: F[:, ti[0], ti[1]])
     del f, p
+
+# batch axis fastest in memory (the reference's own rayon test: [4, 64, 256, 256].f() on a row-major device)
+batch, m = 256, 256
+tp = m * (m + 1) // 2
+nf, npk = batch * m * m, batch * tp
+f = torch.rand(nf, dtype=torch.float64, device="cuda")
+p = torch.empty(npk, dtype=torch.float64, device="cuda")
+rf, rp = dev.wrap(f.data_ptr(), nf, np.float64), dev.wrap(p.data_ptr(), npk, np.float64)
+lf = Layout((batch, m, m), (1, batch, batch * m))
+lp = Layout((batch, tp), (1, batch))
+rep(f"F-layout pack_tril ({batch},{m},{m}) f64", 2 * npk * 8, lambda: dev.pack_tri(rp, lp, rf, lf, "L"))
+rep(f"F-layout unpack_tril Sy ({batch},{m},{m}) f64", (npk + nf) * 8, lambda: dev.unpack_tri(rf, lf, rp, lp, "L", "Sy"))
+rep(f"F-layout unpack_triu Ah ({batch},{m},{m}) f64", (npk + nf) * 8, lambda: dev.unpack_tri(rf, lf, rp, lp, "U", "Ah"))
