@@ -203,6 +203,50 @@ def test_unpack_tri_matches_oracle(dev, dev_col, dtype, n):
                             assert np.array_equal(g, -gt)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("rest", [[8], [5], [4, 6], [6, 3], [16, 2]])
+def test_tri_batch_axis_fastest(dev, dev_col, dtype, rest):
+    """the batch axes are the memory-fastest ones ([.., n, n].f() on a row-major handle and its col-major twin): the
+    run-moving kernels, with every pack width the alignment allows"""
+    rng = np.random.default_rng(seed_of("trirest", rest, np.dtype(dtype).name))
+    for n in (1, 2, 7, 33):
+        n_tp = n * (n + 1) // 2
+        for d, order in ((dev, "row"), (dev_col, "col")):
+            fshape = rest + [n, n] if order == "row" else [n, n] + rest[::-1]
+            pshape = rest + [n_tp] if order == "row" else [n_tp] + rest[::-1]
+            mk = L.f_contig_layout if order == "row" else L.c_contig_layout   # the NON-default order
+            lfull, lpacked = mk(fshape), mk(pshape)
+            full = rng.standard_normal(int(np.prod(fshape))).astype(dtype)
+            tf = rt.Tensor(upload(d, full), P(lfull))
+            for uplo in ("L", "U"):
+                got = tf.pack_tri(uplo)
+                if n > 1:
+                    assert same(got.layout, lpacked)  # the output follows the input's f- / c-preference
+                lpacked = O(got.layout)
+                want = np.zeros(max(lpacked.size, 1), dtype=dtype)
+                oracle.pack_tri(want, lpacked, full, lfull, uplo, order)
+                assert np.array_equal(got.to_numpy(), view_np(want, lpacked))
+                for symm in ("Sy", "Ah", "N"):
+                    out = rt.Tensor(upload(d, np.full(full.size, -5, dtype=dtype)), P(lfull))
+                    d.unpack_tri(out.raw, out.layout, got.raw, got.layout, uplo, symm)
+                    wfull = np.full(full.size, -5, dtype=dtype)
+                    oracle.unpack_tri(wfull, lfull, want, lpacked, uplo, symm, order)
+                    assert np.array_equal(out.to_numpy(), view_np(wfull, lfull)), (order, rest, n, uplo, symm)
+                # sliced batch (offset, odd pitch): narrower packs
+                if rest[0] > 4:
+                    ax = 0 if order == "row" else len(fshape) - 1
+                    sub_f = lfull.narrow(ax, slice(1, None))
+                    tsub = rt.Tensor(tf.raw, P(sub_f))
+                    gp = tsub.pack_tri(uplo)
+                    wp = np.zeros(max(gp.layout.size, 1), dtype=dtype)
+                    oracle.pack_tri(wp, O(gp.layout), full, sub_f, uplo, order)
+                    assert np.array_equal(gp.to_numpy(), view_np(wp, O(gp.layout)))
+                    un = gp.unpack_tri(uplo, "Ay")
+                    wu = np.zeros(max(un.layout.size, 1), dtype=dtype)
+                    oracle.unpack_tri(wu, O(un.layout), wp, O(gp.layout), uplo, "Ay", order)
+                    assert np.array_equal(un.to_numpy(), view_np(wu, O(un.layout)))
+
+
 def test_unpack_tri_n_leaves_other_triangle(dev, dev_col):
     rng = np.random.default_rng(seed_of("unpackN"))
     n, n_tp = 37, 37 * 38 // 2
