@@ -156,3 +156,41 @@ def test_unraveled_arg_all(dev, dev_col):
         tt = t.transpose([2, 0, 1])[::-1]
         vv = v.transpose(2, 0, 1)[::-1]
         assert tt.unraveled_argmax_all() == tuple(int(i) for i in np.unravel_index(np.argmax(vv), vv.shape))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int16])
+@pytest.mark.parametrize("inner", [1, 2, 3, 4, 5, 8, 16])
+def test_many_outputs_short_runs(dev, dev_col, dtype, inner):
+    """(N, 3)-style reductions: a thread owns several outputs (reduce_tiny_kernel) -- all ops, both orders, views"""
+    rng = np.random.default_rng(seed_of("tiny", inner, np.dtype(dtype).name))
+    n = 5003
+    v = (rng.standard_normal((n, inner)) * 50).astype(dtype)
+    for d in (dev, dev_col):
+        t = rt.asarray(v, d)
+        with np.errstate(over="ignore"):
+            got = t.sum_axes(-1).to_numpy()
+            want = v.sum(-1, dtype=dtype)
+        if np.dtype(dtype).kind == "f":
+            assert np.all(np.abs(got - want) <= (1e-12 if dtype == np.float64 else 1e-5) * np.abs(v).sum(-1) + 1e-300)
+        else:
+            assert np.array_equal(got, want)
+        assert np.array_equal(t.max_axes(-1).to_numpy(), v.max(-1))
+        assert np.array_equal(t.min_axes(1).to_numpy(), v.min(1))
+        assert np.array_equal(t.argmax_axes(-1).to_numpy(), np.argmax(v, -1).astype(np.uint64))
+        assert np.array_equal(t.argmin_axes(-1).to_numpy(), np.argmin(v, -1).astype(np.uint64))
+        assert np.array_equal(t.count_nonzero_axes(-1).to_numpy(), np.count_nonzero(v, axis=-1).astype(np.uint64))
+        if np.dtype(dtype).kind == "f":
+            tol = 1e-12 if dtype == np.float64 else 1e-5
+            assert np.all(np.abs(t.mean_axes(-1).to_numpy() - v.mean(-1, dtype=np.float64)) <= tol * np.abs(v).mean(-1) + 1e-300)
+            # the reference's one-pass formula q/n - (s/n)^2 in the element type (auto_impl/reduction.rs:207-317)
+            q = (v * v).sum(-1, dtype=dtype) / dtype(inner)
+            m1 = v.sum(-1, dtype=dtype) / dtype(inner)
+            tol = 1e-12 if dtype == np.float64 else 1e-5
+            assert np.all(np.abs(t.var_axes(-1).to_numpy() - (q - m1 * m1)) <= 4 * tol * q + 1e-300)
+            vv = (v.astype(np.float64) ** 2).sum(-1)
+            assert np.all(np.abs(rt.vecdot(t, t).to_numpy() - vv) <= 4 * tol * vv + 1e-300)
+        # the same through a transposed and a sliced view (short run not contiguous / offset rows)
+        tt = rt.asarray(np.ascontiguousarray(v.T), d).reverse_axes()
+        assert np.array_equal(tt.max_axes(-1).to_numpy(), v.max(-1))
+        ts = t[3:-2]
+        assert np.array_equal(ts.min_axes(-1).to_numpy(), v[3:-2].min(-1))
