@@ -40,8 +40,10 @@ def main():
             if k in d:
                 s[k] = f"{d[k][0]} {d[k][1]}".strip()
         summary[rep] = s
-    with open(os.path.join(out_dir, "r01_ncu_full_summary.json"), "w") as f:
-        json.dump(summary, f, indent=1)
+    # also next to the captures, so a GPU-box run can return the (small) summary and drop the (large) reports
+    for d_out in (out_dir, os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(d_out, "r01_ncu_full_summary.json"), "w") as f:
+            json.dump(summary, f, indent=1)
     for rep, s in summary.items():
         print(rep)
         for k, v in s.items():
