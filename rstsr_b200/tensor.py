@@ -625,6 +625,36 @@ def unstack(t: Tensor, axis: int = 0) -> list:
     return [t[tuple(i if k == axis else slice(None) for k in range(t.ndim))] for i in range(t.shape[axis])]
 
 
+def meshgrid(tensors: Sequence[Tensor], indexing: str = "xy", copy: bool = True) -> list:
+    """rt::meshgrid((tensors, indexing, copy)) (creation_from_tensor.rs:131-207): each 1-D input is reshaped to
+    (1, .., -1, .., 1), broadcast against the others (stride-0 views) and, with `copy`, materialised contiguously in
+    the device's default order -- one strided `assign` from a broadcast source per output."""
+    if indexing not in ("ij", "xy"):
+        raise _ffi.RstsrCudaError(2, "indexing must be 'ij' or 'xy'.")
+    tensors = list(tensors)
+    if not tensors:
+        return []
+    for t in tensors:
+        if t.ndim != 1:
+            raise _ffi.RstsrCudaError(3, "meshgrid only support 1-D tensor.")
+        if not t.device.same_device(tensors[0].device):
+            raise _ffi.RstsrCudaError(5, "All tensors must be on the same device.")
+    if len(tensors) == 1:
+        return [tensors[0].to_contig()] if copy else [tensors[0].view()]
+    nd = len(tensors)
+    shape = [t.shape[0] for t in tensors]
+    if indexing == "xy":
+        shape[0], shape[1] = shape[1], shape[0]
+    outs = []
+    for i, t in enumerate(tensors):
+        ax = (1 if i == 0 else 0 if i == 1 else i) if indexing == "xy" else i
+        stride = [0] * nd
+        stride[ax] = t.stride[0]
+        v = t._with(Layout(tuple(shape), tuple(stride), t.layout.offset))
+        outs.append(v.to_contig(t.device.default_order()) if copy else v)
+    return outs
+
+
 def _diagonal_layout(l: Layout, offset: int) -> Layout:
     """Layout::diagonal(offset, 0, 1) of a 2-D layout (rstsr-common/src/layout/layoutbase.rs:322-384)."""
     d1, d2 = l.shape

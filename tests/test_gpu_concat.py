@@ -114,3 +114,33 @@ def test_concat_large(dev):
     assert np.array_equal(rt.concat(ts, 0).to_numpy(), np.concatenate(arrs, 0))
     assert np.array_equal(rt.concat(ts, 1).to_numpy(), np.concatenate(arrs, 1))
     assert np.array_equal(rt.stack(ts, 2).to_numpy(), np.stack(arrs, 2))
+
+
+def test_meshgrid_matches_numpy(dev, dev_col):
+    """creation_from_tensor/test_meshgrid.rs: 'xy' / 'ij' indexing, copies and broadcast views, 1..4 inputs"""
+    rng = np.random.default_rng(seed_of("mesh"))
+    xs = [rng.standard_normal(n) for n in (5, 3, 4, 2)]
+    for d in (dev, dev_col):
+        ts = [rt.asarray(x, d) for x in xs]
+        for k in (1, 2, 3, 4):
+            for indexing in ("xy", "ij"):
+                want = np.meshgrid(*xs[:k], indexing=indexing)
+                got = rt.meshgrid(ts[:k], indexing)
+                assert len(got) == k
+                for g, w in zip(got, want):
+                    assert g.shape == w.shape and np.array_equal(g.to_numpy(), w)
+                    assert g.layout.c_contig() if d is dev else g.layout.f_contig()
+                views = rt.meshgrid(ts[:k], indexing, copy=False)
+                for g, w in zip(views, want):
+                    assert np.array_equal(g.to_numpy(), w) and g.raw.ptr in [t.raw.ptr for t in ts]
+        # strided / reversed inputs
+        got = rt.meshgrid([ts[0][::-2], ts[1][1:]], "ij")
+        want = np.meshgrid(xs[0][::-2], xs[1][1:], indexing="ij")
+        assert all(np.array_equal(g.to_numpy(), w) for g, w in zip(got, want))
+    assert rt.meshgrid([]) == []
+    with pytest.raises(rt.RstsrCudaError) as e:
+        rt.meshgrid([rt.zeros([2, 2], dev)])
+    assert e.value.kind == "InvalidLayout"
+    with pytest.raises(rt.RstsrCudaError) as e:
+        rt.meshgrid([rt.zeros([2], dev)], "yx")
+    assert e.value.kind == "InvalidValue"
