@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_rows_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // tile kernel.  X = canonical dim 0 (output stride 1), Y = the staged inputs' unit-stride dim.
 // ---------------------------------------------------------------------------------------------
+// smallest extent (of either tile axis) that takes the tile kernel; RC_TILE_MIN is a tuning knob for experiments
+inline int tile_min_extent() {
+    static int v = [] { const char *e = getenv("RC_TILE_MIN"); int x = e ? atoi(e) : 16; return x >= 2 ? x : 16; }();
+    return v;
+}
 constexpr int TILE_X = 64;
 constexpr int TILE_Y = 64;
 constexpr int TILE_WARPS = 8;
@@ -436,13 +441,13 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
 
     // ---- tile path: output contiguous on dim 0, some input contiguous on another dim ----
     if constexpr (ALLOW_TILE && NIN >= 1)
-    if (!vec_ok && c.ndim >= 2 && c.stride[0][0] == 1 && c.shape[0] >= 16) {
+    if (!vec_ok && c.ndim >= 2 && c.stride[0][0] == 1 && c.shape[0] >= tile_min_extent()) {
         int ydim = -1;
         auto unit_dim = [&](int s) {
             if (s < 0) return -1;
             if (c.stride[s][0] == 0 || c.stride[s][0] == 1) return -1;  // already fine along X
             for (int i = 1; i < c.ndim; ++i)
-                if (c.stride[s][i] == 1 && c.shape[i] >= 16) return i;
+                if (c.stride[s][i] == 1 && c.shape[i] >= tile_min_extent()) return i;
             return -1;
         };
         int ya = unit_dim(slot_a), yb = unit_dim(slot_b);

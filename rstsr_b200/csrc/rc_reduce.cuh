@@ -178,7 +178,23 @@ template <class T, bool MAX> struct PArg {
         return (b.i < a.i) ? b : a;
     }
     static __device__ __forceinline__ TO fin(S s, int64_t) { return (uint64_t)s.i; }
+    // In-thread accumulation: every accumulator sees strictly increasing indices, so a strict comparison keeps the
+    // first occurrence and `comb`'s tie / NaN cases reduce to "an empty slot takes anything but a late NaN".
+    static __device__ __forceinline__ void update(S &a, T x, int64_t idx) {
+        const bool better = MAX ? (x > a.v) : (x < a.v);
+        const bool take = (a.i < 0) ? !(isnan_(x) && idx != 0) : better;
+        if (take) { a.v = x; a.i = idx; }
+    }
 };
+
+// acc <- acc (+) element: the policy's fast in-thread update when it has one, otherwise comb(acc, pre(x, idx))
+template <class P, class = void> struct has_update : std::false_type {};
+template <class P> struct has_update<P, std::void_t<decltype(&P::update)>> : std::true_type {};
+template <class P>
+__device__ __forceinline__ void fold(typename P::S &acc, typename P::TI x, int64_t idx) {
+    if constexpr (has_update<P>::value) P::update(acc, x, idx);
+    else acc = P::comb(acc, P::pre(x, idx));
+}
 
 // offset of linear index `i` over dims [first, n) with the given strides (cold path)
 __device__ __noinline__ int64_t decompose_big(int64_t i, int first, int n, const int64_t *shape, const int64_t *stride) {
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 if constexpr (BIN) acc[j] = P::comb(acc[j], P::pre2(p[u].v[j], q[u].v[j], d));
-                else acc[j] = P::comb(acc[j], P::pre(p[u].v[j], (i + (int64_t)u * G) * VEC + j));
+                else fold<P>(acc[j], p[u].v[j], (i + (int64_t)u * G) * VEC + j);
             }
     }
     for (; i < end; i += G) {
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
             for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre2(p.v[j], q.v[j], d));
         } else {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], i * VEC + j));
+            for (int j = 0; j < VEC; ++j) fold<P>(acc[j], p.v[j], i * VEC + j);
         }
     }
     // fold the pack lanes, then the group, in a fixed order
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 if constexpr (BIN) acc[j] = P::comb(acc[j], P::pre2(p[u].v[j], q[u].v[j], d));
-                else acc[j] = P::comb(acc[j], P::pre(p[u].v[j], r + (int64_t)u * RW));
+                else fold<P>(acc[j], p[u].v[j], r + (int64_t)u * RW);
             }
     }
 #pragma unroll 4
@@ -412,7 +428,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
             for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre2(p.v[j], q.v[j], d));
         } else {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = P::comb(acc[j], P::pre(p.v[j], r));
+            for (int j = 0; j < VEC; ++j) fold<P>(acc[j], p.v[j], r);
         }
     }
 #pragma unroll
@@ -487,7 +503,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_tiny_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 if constexpr (BIN) acc[u] = P::comb(acc[u], P::pre2(p[u].v[j], q[u].v[j], d));
-                else acc[u] = P::comb(acc[u], P::pre(p[u].v[j], (int64_t)i * VEC + j));
+                else fold<P>(acc[u], p[u].v[j], (int64_t)i * VEC + j);
             }
     }
 #pragma unroll
