@@ -225,10 +225,19 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_rows_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // tile kernel.  X = canonical dim 0 (output stride 1), Y = the staged inputs' unit-stride dim.
 // ---------------------------------------------------------------------------------------------
-// smallest extent (of either tile axis) that takes the tile kernel; RC_TILE_MIN is a tuning knob for experiments
-inline int tile_min_extent() {
-    static int v = [] { const char *e = getenv("RC_TILE_MIN"); int x = e ? atoi(e) : 16; return x >= 2 ? x : 16; }();
-    return v;
+// Smallest extents that take the tile kernel (tuning knobs RC_TILE_MIN_X / RC_TILE_MIN_Y for experiments):
+//   X = the output's contiguous axis: below it the flat kernel writes short rows just as well,
+//   Y = the staged operand's contiguous axis: reading it with the flat kernel is sector-granular however short it is.
+// Measured (scripts/probe_smalldim.py, k = short extent): output rows shorter than 128 bytes are written as well by
+// the flat kernel (f32 k = 16..24: 3.7 vs 2.5 TB/s), so X >= max(16, 128 / itemsize); a staged axis of 48 bytes or more
+// pays for the tile (f64 k = 8 / 12: 1.6 -> 2.5 / 1.1 -> 3.6 TB/s, f32 k = 12: 1.1 -> 2.0), so Y >= 48 / itemsize.
+inline int tile_min_x(size_t esz) {
+    static int v = [] { const char *e = getenv("RC_TILE_MIN_X"); int x = e ? atoi(e) : 0; return x >= 2 ? x : 0; }();
+    return v ? v : std::max<int>(16, (int)(128 / esz));
+}
+inline int tile_min_y(size_t esz) {
+    static int v = [] { const char *e = getenv("RC_TILE_MIN_Y"); int x = e ? atoi(e) : 0; return x >= 2 ? x : 0; }();
+    return v ? v : std::max<int>(2, (int)((48 + esz - 1) / esz));
 }
 constexpr int TILE_X = 64;
 constexpr int TILE_Y = 64;
@@ -441,13 +450,13 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
 
     // ---- tile path: output contiguous on dim 0, some input contiguous on another dim ----
     if constexpr (ALLOW_TILE && NIN >= 1)
-    if (!vec_ok && c.ndim >= 2 && c.stride[0][0] == 1 && c.shape[0] >= tile_min_extent()) {
+    if (!vec_ok && c.ndim >= 2 && c.stride[0][0] == 1 && c.shape[0] >= tile_min_x(sizeof(TO))) {
         int ydim = -1;
         auto unit_dim = [&](int s) {
             if (s < 0) return -1;
             if (c.stride[s][0] == 0 || c.stride[s][0] == 1) return -1;  // already fine along X
             for (int i = 1; i < c.ndim; ++i)
-                if (c.stride[s][i] == 1 && c.shape[i] >= tile_min_extent()) return i;
+                if (c.stride[s][i] == 1 && c.shape[i] >= tile_min_y(s == slot_a ? sizeof(TA) : sizeof(TB))) return i;
             return -1;
         };
         int ya = unit_dim(slot_a), yb = unit_dim(slot_b);
