@@ -17,7 +17,8 @@
  * The reference itself cannot be compiled here (Rust; no rustc/cargo in the image), so parity is pinned
  * on the reference's own known-answer tests (tests/test_oracle_golden.py) -- see DESIGN.md.
  *
- * Build: gcc -O3 -march=native -fopenmp -shared -fPIC (oracle/Makefile).  The `_par` entry points follow the
+ * Build: gcc -O3 -march=x86-64-v2 -fopenmp -shared -fPIC (oracle/Makefile; bench.py rebuilds a -march=native copy on the
+ * box it times on).  The `_par` entry points follow the
  * rayon regimes with OpenMP threads and are what bench.py times as the CPU baseline (kind "port").
  */
 #include <math.h>
