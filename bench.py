@@ -227,7 +227,7 @@ def run_reference(args, rank):
                              "sample": port.SAMPLE},
             "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "C/OpenMP port of the DeviceFaer loops (the Rust reference cannot be built: no rustc in the image)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -392,7 +392,7 @@ def run_product(args, rank, local_rank, world):
                                     "kind": "port", "sample": port.SAMPLE}
         except Exception as exc:  # the checker is test infrastructure: its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_e2e(args, dev, rt, np, torch, dist, comm, world):
@@ -508,6 +508,25 @@ def run_e2e(args, dev, rt, np, torch, dist, comm, world):
                     "ordered by rc_device_wait, chunked 4/16/4"}
 
 
+_SAVED_STDOUT = None
+
+
+def _guard_stdout():
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is None:
+        sys.stdout.flush()
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    """print the one JSON line on the real stdout"""
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -519,15 +538,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    if world != args.gpus and world == 1 and args.gpus > 1:
-        # launched without torchrun: re-exec under it (one process per GPU)
+    if args.impl != "reference" and world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it (one process per GPU); the children print the line
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
                "--steps", str(args.steps), "--warmup", str(args.warmup)]
         sys.exit(subprocess.call(cmd))
+    # stdout carries exactly one JSON line: whatever a library writes to fd 1 meanwhile (NCCL prints its version
+    # banner there when the box sets NCCL_DEBUG=VERSION) is sent to stderr; emit() restores fd 1 for the line.
+    _guard_stdout()
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
     run_product(args, rank, local_rank, world)
 
 
