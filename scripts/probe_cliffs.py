@@ -114,3 +114,12 @@ for shape in ((1 << 24, 4), (1 << 22, 16), (1 << 20, 100)):
     ta = wrap(a)
     rep(f"sum axis -1 of {shape} f64", a.numel() * 8, lambda: ta.sum_axes(-1), lambda: a.sum(-1))
     rep(f"var axis -1 of {shape} f64", a.numel() * 8, lambda: ta.var_axes(-1), lambda: a.var(-1, unbiased=False))
+
+# ---- misaligned contiguous rows, more dtypes ----
+for dt in (torch.float64, torch.float32, torch.int16):
+    a = rand((8192, 8192), dt)
+    sl = a[:, 1:-1]
+    ts = wrap(sl)
+    nb = sl.numel() * a.element_size()
+    rep(f"sum axis -1 of a[:, 1:-1] {str(dt)[6:]}", nb, lambda: ts.sum_axes(-1), lambda: sl.sum(-1))
+    rep(f"max axis -1 of a[:, 1:-1] {str(dt)[6:]}", nb, lambda: ts.max_axes(-1), lambda: sl.amax(-1))

@@ -194,3 +194,37 @@ def test_many_outputs_short_runs(dev, dev_col, dtype, inner):
         assert np.array_equal(tt.max_axes(-1).to_numpy(), v.max(-1))
         ts = t[3:-2]
         assert np.array_equal(ts.min_axes(-1).to_numpy(), v[3:-2].min(-1))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int16, np.uint8])
+def test_misaligned_contiguous_rows(dev, dtype):
+    """rows that are contiguous but not pack-aligned from their first element (a[:, 1:-1], odd pitch / length):
+    reduce_rows_peel_kernel -- head / aligned body / tail per row, every op"""
+    rng = np.random.default_rng(seed_of("peel", np.dtype(dtype).name))
+    for rows, cols, sl in ((700, 1003, slice(0, None)), (640, 1024, slice(1, -1)), (900, 777, slice(3, None)),
+                           (1200, 4096, slice(5, 4001))):
+        v = (rng.standard_normal((rows, cols)) * 40).astype(dtype)
+        t = rt.asarray(v, dev)[:, sl]
+        w = v[:, sl]
+        with np.errstate(over="ignore"):
+            got, want = t.sum_axes(-1).to_numpy(), w.sum(-1, dtype=dtype)
+        if np.dtype(dtype).kind == "f":
+            tol = 1e-12 if dtype == np.float64 else 1e-5
+            assert np.all(np.abs(got.astype(np.float64) - w.astype(np.float64).sum(-1)) <= tol * np.abs(w).astype(np.float64).sum(-1) + 1e-300)
+            assert np.all(np.abs(t.mean_axes(-1).to_numpy() - w.mean(-1, dtype=np.float64)) <= tol * np.abs(w).mean(-1) + 1e-300)
+        else:
+            assert np.array_equal(got, want)
+        assert np.array_equal(t.max_axes(-1).to_numpy(), w.max(-1))
+        assert np.array_equal(t.min_axes(-1).to_numpy(), w.min(-1))
+        assert np.array_equal(t.argmax_axes(-1).to_numpy(), np.argmax(w, -1).astype(np.uint64))
+        assert np.array_equal(t.argmin_axes(-1).to_numpy(), np.argmin(w, -1).astype(np.uint64))
+        assert np.array_equal(t.count_nonzero_axes(-1).to_numpy(), np.count_nonzero(w, axis=-1).astype(np.uint64))
+    # NaN rules survive the peel: NaN in the head / tail is skipped by max, accepted by argmax only at index 0
+    f = rng.standard_normal((600, 515))
+    f[:, 1] = np.nan
+    f[5, 514] = np.nan
+    tf = rt.asarray(f, dev)[:, 1:]
+    assert np.array_equal(tf.max_axes(-1).to_numpy(), np.nanmax(f[:, 1:], axis=-1))
+    assert np.all(tf.argmax_axes(-1).to_numpy() == 0)   # element 0 of every row is NaN: it sticks (reference rule)
+    tg = rt.asarray(f, dev)[:, 2:]
+    assert np.array_equal(tg.argmax_axes(-1).to_numpy(), np.nanargmax(f[:, 2:], axis=-1).astype(np.uint64))
