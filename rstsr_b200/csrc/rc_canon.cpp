@@ -34,7 +34,7 @@ CanonEw canon_elementwise(const std::vector<const Layout *> &ls, bool collapse_o
             return c;
         }
         if (lo.shape[i] == 1) continue;
-        Dim d;
+        Dim d{};
         d.n = lo.shape[i];
         for (int k = 0; k < c.nops; ++k) d.s[k] = ls[k]->stride[i];
         if (d.s[0] == 0) {

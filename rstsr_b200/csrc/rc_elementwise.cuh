@@ -239,6 +239,11 @@ inline int tile_min_y(size_t esz) {
     static int v = [] { const char *e = getenv("RC_TILE_MIN_Y"); int x = e ? atoi(e) : 0; return x >= 2 ? x : 0; }();
     return v ? v : std::max<int>(2, (int)((48 + esz - 1) / esz));
 }
+// RC_TILE_RECT=0 switches the rectangular-tile kernel off (experiments: the square kernel then takes those shapes)
+inline bool tile_rect_enabled() {
+    static bool v = [] { const char *e = getenv("RC_TILE_RECT"); return !(e && e[0] == '0'); }();
+    return v;
+}
 constexpr int TILE_X = 64;
 constexpr int TILE_Y = 64;
 constexpr int TILE_WARPS = 8;
@@ -360,6 +365,148 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// rectangular tile kernel: one of X / Y is short and the other long.  The square kernel above
+// would leave most of its 64 x 64 slots predicated off (nx = 17: 27 % of the lanes carry data), so here the tile is
+// wx x wy with the short extent taken whole and wx * wy <= 4096, and each role walks the tile by a LINEAR index:
+//   staged operand   i -> (x, y) = divmod(i, wy): consecutive lanes run along Y, its contiguous axis, and wrap
+//                    to the next x, so a short Y still gives full warps;
+//   direct / output  i -> (y, x) = divmod(i, wx): consecutive lanes run along X and wrap to the next y (for an
+//                    output that is contiguous over (y, x) the whole tile is one contiguous run).
+// Same load discipline as the square kernel: 16 slots per thread and operand, all predicated LDGs first.
+// ---------------------------------------------------------------------------------------------
+constexpr int RECT_ELEMS = TILE_X * TILE_Y;
+constexpr int RECT_SLOTS = RECT_ELEMS / (TILE_WARPS * 32);
+constexpr int RECT_LONG = 128;   // smallest long extent
+// Which short extents take this kernel -- measured against the square tile and the flat kernel on (k, n) <-> (n, k)
+// copies (scripts/probe_smalldim.py, profiles/r01_results/probe_smalldim_rect.txt).  The linear walk costs a division
+// per slot and phase, so the kernel is element-rate bound at 5.0-5.3 TB/s (f64) / 2.9-3.1 TB/s (f32) for every k:
+//   short Y (the staged operand's contiguous runs are short): wins for runs of 16 bytes .. 20 elements
+//     (f64 k = 3 / 8 / 17: 3.5 / 2.5 / 4.7 -> 5.2 / 5.2 / 5.0 TB/s; f32 k = 8 / 16: 1.6 / 2.6 -> 3.1 TB/s); from k = 24
+//     the square tile is ahead again (f64 5.6 vs 5.1);
+//   short X (short output rows): only 8-byte elements with 16 <= k <= 20 (4.5 -> 5.2 / 4.9 TB/s); below that the flat
+//     kernel writes the short rows at 6.2-6.4 TB/s, and 4-byte rows are better off flat (3.75 TB/s) up to k = 24.
+// 1- and 2-byte elements keep their previous paths (not measured).
+inline bool rect_short_y(uint32_t nx, uint32_t ny, size_t esz) {
+    return tile_rect_enabled() && esz >= 4 && ny <= 20 && (size_t)ny * esz >= 16 && nx >= (uint32_t)RECT_LONG;
+}
+inline bool rect_short_x(uint32_t nx, uint32_t ny, size_t esz) {
+    return tile_rect_enabled() && esz == 8 && nx >= 16 && nx <= 20 && ny >= (uint32_t)RECT_LONG;
+}
+
+struct TileRectDesc : TileDesc {
+    uint32_t wx, wy;         // tile extents along X and Y (wx * wy <= RECT_ELEMS)
+    uint32_t pitch;          // shared-memory row pitch (elements) of a staged tile: s[x * pitch + y]
+    FastDiv div_wx, div_wy;
+};
+
+__device__ __forceinline__ uint32_t rect_tid() {
+    uint32_t t = threadIdx.x;
+    asm volatile("" : "+r"(t));  // opaque to common-subexpression elimination
+    return t;
+}
+
+template <class F>
+__global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_rect_kernel(const __grid_constant__ TileRectDesc d,
+                                                                        typename F::TO *c, const typename F::TA *a,
+                                                                        const typename F::TB *b, int mode_a, int mode_b,
+                                                                        EwConst<typename F::TA> ka,
+                                                                        EwConst<typename F::TB> kb) {
+    using TA = typename F::TA;
+    using TB = typename F::TB;
+    using TO = typename F::TO;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TA *sa = reinterpret_cast<TA *>(smem_raw);
+    TB *sb = reinterpret_cast<TB *>(
+        smem_raw + ((mode_a == TILE_STAGED) ? ((sizeof(TA) * d.wx * d.pitch + 15) & ~(size_t)15) : 0));
+
+    uint32_t t = blockIdx.x, ty, tx;
+    d.div_ty.divmod(t, t, ty);
+    d.div_tx.divmod(t, t, tx);
+    int64_t base[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < KMAXD; ++i) {
+        if (i >= d.nbatch) break;
+        uint32_t q, r;
+        d.bdiv[i].divmod(t, q, r);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) base[k] += (int64_t)r * d.bstride[k][i];
+        t = q;
+    }
+    const uint32_t x0 = tx * d.wx, y0 = ty * d.wy;
+    const uint32_t ex = min(d.wx, d.nx - x0), ey = min(d.wy, d.ny - y0);  // valid extent of this tile
+
+    const bool stg_a = (F::NIN >= 1) && mode_a == TILE_STAGED, dir_a = (F::NIN >= 1) && mode_a == TILE_DIRECT;
+    const bool stg_b = (F::NIN >= 2) && mode_b == TILE_STAGED, dir_b = (F::NIN >= 2) && mode_b == TILE_DIRECT;
+    const TA *pa = a + base[1] + (int64_t)x0 * d.sx[1] + (int64_t)y0 * d.sy[1];
+    const TB *pb = b + base[2] + (int64_t)x0 * d.sx[2] + (int64_t)y0 * d.sy[2];
+
+    // Slot coordinates are recomputed in every phase from a laundered thread index: kept live across the phases
+    // (the compiler's choice when it can prove them equal) they cost 64 registers and half the occupancy.
+    Pack<TA, 1> ra[RECT_SLOTS];
+    Pack<TB, 1> rb[RECT_SLOTS];
+    if constexpr (F::NIN >= 1) {
+        const FastDiv dv = stg_a ? d.div_wy : d.div_wx;
+        const uint32_t tid = rect_tid();
+#pragma unroll
+        for (int s = 0; s < RECT_SLOTS; ++s) {
+            uint32_t q, r;
+            dv.divmod(tid + s * (TILE_WARPS * 32), q, r);
+            const uint32_t x = stg_a ? q : r, y = stg_a ? r : q;
+            ra[s].v[0] = ka.v;
+            ld_stream_pred<TA, 1>(ra[s], pa + (int64_t)x * d.sx[1] + (int64_t)y * d.sy[1],
+                                  (stg_a || dir_a) && x < ex && y < ey);
+        }
+    }
+    if constexpr (F::NIN >= 2) {
+        const FastDiv dv = stg_b ? d.div_wy : d.div_wx;
+        const uint32_t tid = rect_tid();
+#pragma unroll
+        for (int s = 0; s < RECT_SLOTS; ++s) {
+            uint32_t q, r;
+            dv.divmod(tid + s * (TILE_WARPS * 32), q, r);
+            const uint32_t x = stg_b ? q : r, y = stg_b ? r : q;
+            rb[s].v[0] = kb.v;
+            ld_stream_pred<TB, 1>(rb[s], pb + (int64_t)x * d.sx[2] + (int64_t)y * d.sy[2],
+                                  (stg_b || dir_b) && x < ex && y < ey);
+        }
+    }
+    if (stg_a || stg_b) {
+        const uint32_t tid = rect_tid();
+#pragma unroll
+        for (int s = 0; s < RECT_SLOTS; ++s) {
+            uint32_t xs, ys;
+            d.div_wy.divmod(tid + s * (TILE_WARPS * 32), xs, ys);
+            if (xs < ex && ys < ey) {  // also keeps the slot inside the wx x pitch array
+                if constexpr (F::NIN >= 1)
+                    if (stg_a) sa[xs * d.pitch + ys] = ra[s].v[0];
+                if constexpr (F::NIN >= 2)
+                    if (stg_b) sb[xs * d.pitch + ys] = rb[s].v[0];
+            }
+        }
+    }
+    __syncthreads();
+
+    TO *pc = c + base[0] + (int64_t)y0 * d.sy[0] + x0;
+    const uint32_t tid = rect_tid();
+#pragma unroll
+    for (int s = 0; s < RECT_SLOTS; ++s) {
+        uint32_t yd, xd;
+        d.div_wx.divmod(tid + s * (TILE_WARPS * 32), yd, xd);
+        if (yd < ey && xd < ex) {
+            const TA va = stg_a ? sa[xd * d.pitch + yd] : ra[s].v[0];
+            TO out;
+            if constexpr (F::NIN > 1) {
+                const TB vb = stg_b ? sb[xd * d.pitch + yd] : rb[s].v[0];
+                out = F::apply(va, vb);
+            } else {
+                out = F::apply(va);
+            }
+            __stcs(pc + (int64_t)yd * d.sy[0] + xd, out);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
 struct EwArgs {
@@ -456,7 +603,11 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
             if (s < 0) return -1;
             if (c.stride[s][0] == 0 || c.stride[s][0] == 1) return -1;  // already fine along X
             for (int i = 1; i < c.ndim; ++i)
-                if (c.stride[s][i] == 1 && c.shape[i] >= tile_min_y(s == slot_a ? sizeof(TA) : sizeof(TB))) return i;
+                if (c.stride[s][i] == 1 && (c.shape[i] >= tile_min_y(s == slot_a ? sizeof(TA) : sizeof(TB)) ||
+                                            rect_short_y((uint32_t)std::min<int64_t>(c.shape[0], 1u << 30),
+                                                         (uint32_t)std::min<int64_t>(c.shape[i], 1u << 30),
+                                                         s == slot_a ? sizeof(TA) : sizeof(TB))))
+                    return i;
             return -1;
         };
         int ya = unit_dim(slot_a), yb = unit_dim(slot_b);
@@ -491,6 +642,43 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                 int tm_a = TILE_CONST, tm_b = TILE_CONST;
                 if (slot_a >= 0) tm_a = (c.stride[slot_a][ydim] == 1 && c.stride[slot_a][0] > 1 && ya == ydim) ? TILE_STAGED : TILE_DIRECT;
                 if (slot_b >= 0) tm_b = (c.stride[slot_b][ydim] == 1 && c.stride[slot_b][0] > 1 && yb == ydim) ? TILE_STAGED : TILE_DIRECT;
+                // one short and one long extent: rectangular tile, the short extent taken whole
+                const size_t esz_staged = (ya == ydim && slot_a >= 0) ? sizeof(TA) : sizeof(TB);
+                if (rect_short_y(t.nx, t.ny, esz_staged) || rect_short_x(t.nx, t.ny, sizeof(TO))) {
+                    TileRectDesc r;
+                    std::memset(&r, 0, sizeof(r));
+                    static_cast<TileDesc &>(r) = t;
+                    if (t.nx <= t.ny) {
+                        r.wx = t.nx;
+                        r.wy = std::min<uint32_t>(t.ny, (uint32_t)(RECT_ELEMS / r.wx) & ~31u);
+                        r.pitch = r.wy + ((31u - (r.wy & 31u)) & 31u);  // pitch = 31 (mod 32): lanes that wrap to the
+                                                                        // next y miss the banks of the first ones
+                    } else {
+                        r.wy = t.ny;
+                        r.wx = std::min<uint32_t>(t.nx, (uint32_t)(RECT_ELEMS / r.wy) & ~31u);
+                        r.pitch = r.wy | 1u;
+                    }
+                    r.tiles_x = (t.nx + r.wx - 1) / r.wx;
+                    r.tiles_y = (t.ny + r.wy - 1) / r.wy;
+                    r.div_tx = FastDiv(r.tiles_x);
+                    r.div_ty = FastDiv(r.tiles_y);
+                    r.div_wx = FastDiv(r.wx);
+                    r.div_wy = FastDiv(r.wy);
+                    int64_t rect_tiles = (int64_t)r.tiles_x * r.tiles_y * nb;
+                    if (rect_tiles < (1ll << 31)) {
+                        r.total_tiles = (uint32_t)rect_tiles;
+                        size_t smem = 0;
+                        if (tm_a == TILE_STAGED) smem += (sizeof(TA) * r.wx * r.pitch + 15) & ~(size_t)15;
+                        if (tm_b == TILE_STAGED) smem += (sizeof(TB) * r.wx * r.pitch + 15) & ~(size_t)15;
+                        if (smem > 48 * 1024)
+                            RC_CUDA(cudaFuncSetAttribute(ew_tile_rect_kernel<F>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        ew_tile_rect_kernel<F><<<r.total_tiles, TILE_WARPS * 32, smem, dev->stream>>>(r, pc, pa, pb, tm_a,
+                                                                                                    tm_b, ka, kb);
+                        after_launch(dev, "ew_tile_rect_kernel");
+                        return;
+                    }
+                }
                 size_t smem = 0;
                 if (tm_a == TILE_STAGED) smem += sizeof(TA) * TILE_X * (TILE_Y + 1);
                 if (tm_b == TILE_STAGED) smem += sizeof(TB) * TILE_X * (TILE_Y + 1);

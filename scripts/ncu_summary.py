@@ -41,8 +41,9 @@ def main():
                 s[k] = f"{d[k][0]} {d[k][1]}".strip()
         summary[rep] = s
     # also next to the captures, so a GPU-box run can return the (small) summary and drop the (large) reports
+    out_name = sys.argv[1] if len(sys.argv) > 1 else "r01_ncu_full_summary.json"  # a second name keeps later captures apart
     for d_out in (out_dir, os.path.join(ROOT, "gpurun_out")):
-        with open(os.path.join(d_out, "r01_ncu_full_summary.json"), "w") as f:
+        with open(os.path.join(d_out, out_name), "w") as f:
             json.dump(summary, f, indent=1)
     for rep, s in summary.items():
         print(rep)

@@ -82,6 +82,9 @@ tcol, trow = wrap(col), wrap(row)
 rep("outer sum (n,1)+(1,n) f64", n * n * 8, lambda: tcol + trow, lambda: col + row)
 m = rand((n, n), torch.float64)
 tm = wrap(m)
+scratch = rand((n, n), torch.float64)
+tscr = wrap(scratch)
+rep("fill (n,n) f64 (write-only)", n * n * 8, lambda: tscr.fill(1.5), lambda: scratch.fill_(1.5))
 rep("(n,n) * (n,1) f64", 2 * n * n * 8, lambda: tm * tcol, lambda: m * col)
 rep("(n,n).T + (n,n) f64", 3 * n * n * 8, lambda: wrap(m.t()) + tm, lambda: m.t() + m)
 rep("(n,n).T + (n,n).T f64", 3 * n * n * 8, lambda: wrap(m.t()) + wrap(m.t()), lambda: m.t() + m.t())

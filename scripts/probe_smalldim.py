@@ -12,7 +12,7 @@ torch.cuda.set_device(0)
 dev = rt.DeviceCuda(0, rt.ROW_MAJOR, stream=torch.cuda.current_stream().cuda_stream)
 
 
-def timeit(fn, iters=10, warmup=2):
+def timeit(fn, iters=8, warmup=2):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -27,7 +27,7 @@ def timeit(fn, iters=10, warmup=2):
 
 for tdt, ndt in ((torch.float64, np.float64), (torch.float32, np.float32)):
     item = np.dtype(ndt).itemsize
-    for k in (8, 12, 16, 17, 24, 32, 48, 64, 100):
+    for k in (3, 4, 6, 8, 12, 16, 17, 24, 32, 48, 64, 100):
         n = (1 << 25) // k
         src = torch.rand(k * n, dtype=tdt, device="cuda")
         dst = torch.empty(k * n, dtype=tdt, device="cuda")

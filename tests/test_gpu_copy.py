@@ -168,6 +168,14 @@ COPY_SHAPES = [
     ("4-D (3,1,0,2)", (6, 17, 9, 70), (3, 1, 0, 2)),
     ("thin", (2, 100000), (1, 0)),
     ("ragged tiles", (65, 129), (1, 0)),
+    # one short and one long extent: ew_tile_rect_kernel (short extent whole, linear walk of the tile)
+    ("rect narrow X=17", (17, 1000), (1, 0)),
+    ("rect narrow X=40", (40, 700), (1, 0)),
+    ("rect narrow Y=17", (1000, 17), (1, 0)),
+    ("rect narrow Y=48", (700, 48), (1, 0)),
+    ("rect narrow X batched ragged", (3, 20, 300), (0, 2, 1)),
+    ("rect narrow Y batched ragged", (3, 300, 20), (0, 2, 1)),
+    ("rect narrow Y=7 long X", (5000, 7), (1, 0)),
 ]
 
 

@@ -301,6 +301,11 @@ KERNEL_SHAPES = [
     ("tile kernel a + b^T", (96, 160), None, "T"),
     ("tile kernel batched", (3, 70, 90), None, "T3"),
     ("short rows", (4096, 6), None, (0, 1)),
+    ("rect tile a + b^T, narrow X=17", (1000, 17), None, "T"),
+    ("rect tile a + b^T, narrow X=40", (700, 40), None, "T"),
+    ("rect tile a + b^T, narrow Y=24", (24, 900), None, "T"),
+    ("rect tile batched, narrow X", (3, 310, 33), None, "T3"),
+    ("rect tile batched, narrow Y", (3, 18, 333), None, "T3"),
 ]
 
 
