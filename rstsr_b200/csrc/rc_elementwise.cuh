@@ -378,31 +378,122 @@ constexpr int RECT_ELEMS = TILE_X * TILE_Y;
 constexpr int RECT_SLOTS = RECT_ELEMS / (TILE_WARPS * 32);
 constexpr int RECT_LONG = 128;   // smallest long extent
 // Which short extents take this kernel -- measured against the square tile and the flat kernel on (k, n) <-> (n, k)
-// copies (scripts/probe_smalldim.py, profiles/r01_results/probe_smalldim_rect.txt).  The linear walk costs a division
-// per slot and phase, so the kernel is element-rate bound at 5.0-5.3 TB/s (f64) / 2.9-3.1 TB/s (f32) for every k:
-//   short Y (the staged operand's contiguous runs are short): wins for runs of 16 bytes .. 20 elements
-//     (f64 k = 3 / 8 / 17: 3.5 / 2.5 / 4.7 -> 5.2 / 5.2 / 5.0 TB/s; f32 k = 8 / 16: 1.6 / 2.6 -> 3.1 TB/s); from k = 24
-//     the square tile is ahead again (f64 5.6 vs 5.1);
-//   short X (short output rows): only 8-byte elements with 16 <= k <= 20 (4.5 -> 5.2 / 4.9 TB/s); below that the flat
-//     kernel writes the short rows at 6.2-6.4 TB/s, and 4-byte rows are better off flat (3.75 TB/s) up to k = 24.
+// copies (scripts/probe_smalldim.py; profiles/r01_results/probe_smalldim_rect*.txt).  The linear walk costs a division
+// per slot and phase: ~40 instructions per element, so 8-byte elements reach the DRAM bound (6.1-6.4 TB/s for every
+// k <= 32) and 4-byte elements are issue-bound at 4.1-4.35 TB/s.
+//   short Y (the staged operand's contiguous runs are short), runs of 16 bytes .. 32 (f64) / 31 (f32) elements:
+//     f64 k = 3 / 8 / 17 / 24: 3.5 / 2.5 / 4.7 / 5.6 -> 6.4 / 6.4 / 6.2 / 6.1 TB/s; f32 k = 8 / 16 / 24: 1.6 / 2.6 / 3.7 ->
+//     4.4 / 4.3 / 4.1 TB/s; from k = 32 (f32) / 48 (f64) the square tile is ahead;
+//   short X (short output rows): f64 16 <= k <= 31 (k = 16 / 24: 4.5 / 5.5 -> 6.4 / 6.2 TB/s; below 16 the flat kernel
+//     writes the rows at 6.2-6.4 TB/s), f32 3 <= k <= 31 (flat 3.75 -> 4.1-4.25 TB/s).
 // 1- and 2-byte elements keep their previous paths (not measured).
+inline int rect_knob(const char *name, int dflt) {  // experiments only
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 inline bool rect_short_y(uint32_t nx, uint32_t ny, size_t esz) {
-    return tile_rect_enabled() && esz >= 4 && ny <= 20 && (size_t)ny * esz >= 16 && nx >= (uint32_t)RECT_LONG;
+    static const int max8 = rect_knob("RC_RECT_MAX_Y8", 32), max4 = rect_knob("RC_RECT_MAX_Y4", 31);
+    return tile_rect_enabled() && (esz == 8 || esz == 4) && ny <= (uint32_t)(esz == 8 ? max8 : max4) &&
+           (size_t)ny * esz >= 16 && nx >= (uint32_t)RECT_LONG;
 }
 inline bool rect_short_x(uint32_t nx, uint32_t ny, size_t esz) {
-    return tile_rect_enabled() && esz == 8 && nx >= 16 && nx <= 20 && ny >= (uint32_t)RECT_LONG;
+    static const int lo8 = rect_knob("RC_RECT_X_LO8", 16), hi8 = rect_knob("RC_RECT_X_HI8", 31);
+    static const int lo4 = rect_knob("RC_RECT_X_LO4", 3), hi4 = rect_knob("RC_RECT_X_HI4", 31);
+    const uint32_t lo = esz == 8 ? lo8 : lo4, hi = esz == 8 ? hi8 : hi4;
+    return tile_rect_enabled() && (esz == 8 || esz == 4) && nx >= lo && nx <= hi && ny >= (uint32_t)RECT_LONG;
 }
 
 struct TileRectDesc : TileDesc {
     uint32_t wx, wy;         // tile extents along X and Y (wx * wy <= RECT_ELEMS)
     uint32_t pitch;          // shared-memory row pitch (elements) of a staged tile: s[x * pitch + y]
     FastDiv div_wx, div_wy;
+    int32_t sx32[3], sy32[3];  // sx / sy again: offsets inside one tile fit 32 bits (checked by the launcher)
 };
 
 __device__ __forceinline__ uint32_t rect_tid() {
     uint32_t t = threadIdx.x;
     asm volatile("" : "+r"(t));  // opaque to common-subexpression elimination
     return t;
+}
+
+// all loads of one operand of the rectangular tile: staged role (x, y) = divmod(i, wy) with unit stride along Y,
+// direct role (y, x) = divmod(i, wx); a constant operand keeps `kv`
+template <class T>
+__device__ __forceinline__ void rect_load(Pack<T, 1> (&r)[RECT_SLOTS], const T *p, T kv, bool staged, bool direct,
+                                          const TileRectDesc &d, int k, uint32_t ex, uint32_t ey) {
+    const uint32_t tid = rect_tid();
+#pragma unroll
+    for (int s = 0; s < RECT_SLOTS; ++s) r[s].v[0] = kv;
+    if (staged) {
+        const int32_t sx = d.sx32[k];
+#pragma unroll
+        for (int s = 0; s < RECT_SLOTS; ++s) {
+            uint32_t x, y;
+            d.div_wy.divmod(tid + s * (TILE_WARPS * 32), x, y);
+            ld_stream_pred<T, 1>(r[s], p + ((int32_t)x * sx + (int32_t)y), x < ex && y < ey);
+        }
+    } else if (direct) {
+        const int32_t sx = d.sx32[k], sy = d.sy32[k];
+#pragma unroll
+        for (int s = 0; s < RECT_SLOTS; ++s) {
+            uint32_t x, y;
+            d.div_wx.divmod(tid + s * (TILE_WARPS * 32), y, x);
+            ld_stream_pred<T, 1>(r[s], p + ((int32_t)y * sy + (int32_t)x * sx), x < ex && y < ey);
+        }
+    }
+}
+
+// shared-memory accessors by 32-bit shared-window address (the compiler re-derived the window base and re-read the
+// pitch from the parameters for every slot when handed a pointer)
+template <class T>
+__device__ __forceinline__ void rect_sts(uint32_t addr, const T &v) {
+    if constexpr (sizeof(T) == 8) {
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(*reinterpret_cast<const unsigned long long *>(&v)) : "memory");
+    } else if constexpr (sizeof(T) == 4) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const unsigned int *>(&v)) : "memory");
+    } else if constexpr (sizeof(T) == 2) {
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short *>(&v)) : "memory");
+    } else {
+        static_assert(sizeof(T) == 1, "element size");
+        const unsigned short t = *reinterpret_cast<const unsigned char *>(&v);
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "h"(t) : "memory");
+    }
+}
+template <class T>
+__device__ __forceinline__ T rect_lds(uint32_t addr) {
+    T v;
+    if constexpr (sizeof(T) == 8) {
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(*reinterpret_cast<unsigned long long *>(&v)) : "r"(addr) : "memory");
+    } else if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(*reinterpret_cast<unsigned int *>(&v)) : "r"(addr) : "memory");
+    } else if constexpr (sizeof(T) == 2) {
+        asm volatile("ld.shared.b16 %0, [%1];" : "=h"(*reinterpret_cast<unsigned short *>(&v)) : "r"(addr) : "memory");
+    } else {
+        static_assert(sizeof(T) == 1, "element size");
+        unsigned short t;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=h"(t) : "r"(addr) : "memory");
+        *reinterpret_cast<unsigned char *>(&v) = (unsigned char)t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t rect_keep(uint32_t v) {
+    asm volatile("" : "+r"(v));  // pinned in a register
+    return v;
+}
+
+// registers of a staged operand -> shared memory s[x * pitch + y], same walk as its loads
+template <class T>
+__device__ __forceinline__ void rect_stage(uint32_t sm, const Pack<T, 1> (&r)[RECT_SLOTS], const TileRectDesc &d,
+                                           uint32_t ex, uint32_t ey) {
+    const uint32_t tid = rect_tid();
+    const uint32_t pitch = rect_keep(d.pitch);
+#pragma unroll
+    for (int s = 0; s < RECT_SLOTS; ++s) {
+        uint32_t x, y;
+        d.div_wy.divmod(tid + s * (TILE_WARPS * 32), x, y);
+        if (x < ex && y < ey)  // also keeps the slot inside the wx x pitch array
+            rect_sts<T>(sm + (x * pitch + y) * (uint32_t)sizeof(T), r[s].v[0]);
+    }
 }
 
 template <class F>
@@ -415,9 +506,10 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_rect_kernel(const __g
     using TB = typename F::TB;
     using TO = typename F::TO;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TA *sa = reinterpret_cast<TA *>(smem_raw);
-    TB *sb = reinterpret_cast<TB *>(
-        smem_raw + ((mode_a == TILE_STAGED) ? ((sizeof(TA) * d.wx * d.pitch + 15) & ~(size_t)15) : 0));
+    // staged tiles by shared-window address: a at the start, b behind it (16-byte aligned)
+    const uint32_t sa = rect_keep((uint32_t)__cvta_generic_to_shared(smem_raw));
+    const uint32_t sb = rect_keep(
+        sa + ((mode_a == TILE_STAGED) ? (((uint32_t)sizeof(TA) * d.wx * d.pitch + 15u) & ~15u) : 0u));
 
     uint32_t t = blockIdx.x, ty, tx;
     d.div_ty.divmod(t, t, ty);
@@ -442,67 +534,41 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_rect_kernel(const __g
 
     // Slot coordinates are recomputed in every phase from a laundered thread index: kept live across the phases
     // (the compiler's choice when it can prove them equal) they cost 64 registers and half the occupancy.
+    // Index arithmetic is what bounds this kernel (first version: 68 instructions per element, 32 % of them IMAD,
+    // issue-active 65-75 % at 30-55 % DRAM -- profiles/r01_ncu_rect_summary.json), hence 32-bit offsets inside the
+    // tile, the known unit strides (staged: along Y, output: along X) and one loop per role.
     Pack<TA, 1> ra[RECT_SLOTS];
     Pack<TB, 1> rb[RECT_SLOTS];
-    if constexpr (F::NIN >= 1) {
-        const FastDiv dv = stg_a ? d.div_wy : d.div_wx;
-        const uint32_t tid = rect_tid();
-#pragma unroll
-        for (int s = 0; s < RECT_SLOTS; ++s) {
-            uint32_t q, r;
-            dv.divmod(tid + s * (TILE_WARPS * 32), q, r);
-            const uint32_t x = stg_a ? q : r, y = stg_a ? r : q;
-            ra[s].v[0] = ka.v;
-            ld_stream_pred<TA, 1>(ra[s], pa + (int64_t)x * d.sx[1] + (int64_t)y * d.sy[1],
-                                  (stg_a || dir_a) && x < ex && y < ey);
-        }
-    }
-    if constexpr (F::NIN >= 2) {
-        const FastDiv dv = stg_b ? d.div_wy : d.div_wx;
-        const uint32_t tid = rect_tid();
-#pragma unroll
-        for (int s = 0; s < RECT_SLOTS; ++s) {
-            uint32_t q, r;
-            dv.divmod(tid + s * (TILE_WARPS * 32), q, r);
-            const uint32_t x = stg_b ? q : r, y = stg_b ? r : q;
-            rb[s].v[0] = kb.v;
-            ld_stream_pred<TB, 1>(rb[s], pb + (int64_t)x * d.sx[2] + (int64_t)y * d.sy[2],
-                                  (stg_b || dir_b) && x < ex && y < ey);
-        }
-    }
-    if (stg_a || stg_b) {
-        const uint32_t tid = rect_tid();
-#pragma unroll
-        for (int s = 0; s < RECT_SLOTS; ++s) {
-            uint32_t xs, ys;
-            d.div_wy.divmod(tid + s * (TILE_WARPS * 32), xs, ys);
-            if (xs < ex && ys < ey) {  // also keeps the slot inside the wx x pitch array
-                if constexpr (F::NIN >= 1)
-                    if (stg_a) sa[xs * d.pitch + ys] = ra[s].v[0];
-                if constexpr (F::NIN >= 2)
-                    if (stg_b) sb[xs * d.pitch + ys] = rb[s].v[0];
-            }
-        }
-    }
+    if constexpr (F::NIN >= 1) rect_load<TA>(ra, pa, ka.v, stg_a, dir_a, d, 1, ex, ey);
+    if constexpr (F::NIN >= 2) rect_load<TB>(rb, pb, kb.v, stg_b, dir_b, d, 2, ex, ey);
+    if constexpr (F::NIN >= 1)
+        if (stg_a) rect_stage<TA>(sa, ra, d, ex, ey);
+    if constexpr (F::NIN >= 2)
+        if (stg_b) rect_stage<TB>(sb, rb, d, ex, ey);
     __syncthreads();
 
+    // phase 2: (y, x) = divmod(i, wx).  No branch around a slot: an invalid slot reads shared-memory word 0 and
+    // skips only its store (branches cost a convergence barrier and a re-derived base pointer per slot).
     TO *pc = c + base[0] + (int64_t)y0 * d.sy[0] + x0;
+    asm volatile("" : "+l"(pc));  // materialised once, not re-derived per slot
     const uint32_t tid = rect_tid();
+    const int32_t syc = d.sy32[0];
+    const uint32_t pitch = rect_keep(d.pitch);
 #pragma unroll
     for (int s = 0; s < RECT_SLOTS; ++s) {
         uint32_t yd, xd;
         d.div_wx.divmod(tid + s * (TILE_WARPS * 32), yd, xd);
-        if (yd < ey && xd < ex) {
-            const TA va = stg_a ? sa[xd * d.pitch + yd] : ra[s].v[0];
-            TO out;
-            if constexpr (F::NIN > 1) {
-                const TB vb = stg_b ? sb[xd * d.pitch + yd] : rb[s].v[0];
-                out = F::apply(va, vb);
-            } else {
-                out = F::apply(va);
-            }
-            __stcs(pc + (int64_t)yd * d.sy[0] + xd, out);
+        const bool ok = yd < ey && xd < ex;
+        const uint32_t si = ok ? xd * pitch + yd : 0u;
+        const TA va = stg_a ? rect_lds<TA>(sa + si * (uint32_t)sizeof(TA)) : ra[s].v[0];
+        TO out;
+        if constexpr (F::NIN > 1) {
+            const TB vb = stg_b ? rect_lds<TB>(sb + si * (uint32_t)sizeof(TB)) : rb[s].v[0];
+            out = F::apply(va, vb);
+        } else {
+            out = F::apply(va);
         }
+        if (ok) __stcs(pc + ((int32_t)yd * syc + (int32_t)xd), out);
     }
 }
 
@@ -597,17 +663,22 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
 
     // ---- tile path: output contiguous on dim 0, some input contiguous on another dim ----
     if constexpr (ALLOW_TILE && NIN >= 1)
-    if (!vec_ok && c.ndim >= 2 && c.stride[0][0] == 1 && c.shape[0] >= tile_min_x(sizeof(TO))) {
+    if (!vec_ok && c.ndim >= 2 && c.stride[0][0] == 1) {
         int ydim = -1;
+        // the square tile needs both extents above its thresholds; the rectangular one takes its own shapes
+        const bool square_x_ok = c.shape[0] >= tile_min_x(sizeof(TO));
+        const uint32_t nx32 = (uint32_t)std::min<int64_t>(c.shape[0], 1u << 30);
         auto unit_dim = [&](int s) {
             if (s < 0) return -1;
             if (c.stride[s][0] == 0 || c.stride[s][0] == 1) return -1;  // already fine along X
-            for (int i = 1; i < c.ndim; ++i)
-                if (c.stride[s][i] == 1 && (c.shape[i] >= tile_min_y(s == slot_a ? sizeof(TA) : sizeof(TB)) ||
-                                            rect_short_y((uint32_t)std::min<int64_t>(c.shape[0], 1u << 30),
-                                                         (uint32_t)std::min<int64_t>(c.shape[i], 1u << 30),
-                                                         s == slot_a ? sizeof(TA) : sizeof(TB))))
+            const size_t esz = s == slot_a ? sizeof(TA) : sizeof(TB);
+            for (int i = 1; i < c.ndim; ++i) {
+                if (c.stride[s][i] != 1) continue;
+                const uint32_t ny32 = (uint32_t)std::min<int64_t>(c.shape[i], 1u << 30);
+                if ((square_x_ok && c.shape[i] >= tile_min_y(esz)) || rect_short_y(nx32, ny32, esz) ||
+                    rect_short_x(nx32, ny32, sizeof(TO)))
                     return i;
+            }
             return -1;
         };
         int ya = unit_dim(slot_a), yb = unit_dim(slot_b);
@@ -665,7 +736,15 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                     r.div_wx = FastDiv(r.wx);
                     r.div_wy = FastDiv(r.wy);
                     int64_t rect_tiles = (int64_t)r.tiles_x * r.tiles_y * nb;
-                    if (rect_tiles < (1ll << 31)) {
+                    bool fits32 = true;  // offsets inside one tile as 32-bit integers
+                    for (int k = 0; k < 3; ++k) {
+                        const int64_t ax = t.sx[k] < 0 ? -t.sx[k] : t.sx[k], ay = t.sy[k] < 0 ? -t.sy[k] : t.sy[k];
+                        fits32 = fits32 && ax < (1ll << 31) && ay < (1ll << 31) &&
+                                 (int64_t)(r.wx - 1) * ax + (int64_t)(r.wy - 1) * ay < (1ll << 31);
+                        r.sx32[k] = (int32_t)t.sx[k];
+                        r.sy32[k] = (int32_t)t.sy[k];
+                    }
+                    if (rect_tiles < (1ll << 31) && fits32) {
                         r.total_tiles = (uint32_t)rect_tiles;
                         size_t smem = 0;
                         if (tm_a == TILE_STAGED) smem += (sizeof(TA) * r.wx * r.pitch + 15) & ~(size_t)15;
@@ -679,15 +758,17 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                         return;
                     }
                 }
-                size_t smem = 0;
-                if (tm_a == TILE_STAGED) smem += sizeof(TA) * TILE_X * (TILE_Y + 1);
-                if (tm_b == TILE_STAGED) smem += sizeof(TB) * TILE_X * (TILE_Y + 1);
-                if (smem > 48 * 1024)  // opt in to > 48 KB dynamic shared memory (per device)
-                    RC_CUDA(cudaFuncSetAttribute(ew_tile_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem));
-                ew_tile_kernel<F><<<t.total_tiles, TILE_WARPS * 32, smem, dev->stream>>>(t, pc, pa, pb, tm_a, tm_b, ka, kb);
-                after_launch(dev, "ew_tile_kernel");
-                return;
+                if (square_x_ok && t.ny >= (uint32_t)tile_min_y(esz_staged)) {
+                    size_t smem = 0;
+                    if (tm_a == TILE_STAGED) smem += sizeof(TA) * TILE_X * (TILE_Y + 1);
+                    if (tm_b == TILE_STAGED) smem += sizeof(TB) * TILE_X * (TILE_Y + 1);
+                    if (smem > 48 * 1024)  // opt in to > 48 KB dynamic shared memory (per device)
+                        RC_CUDA(cudaFuncSetAttribute(ew_tile_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)smem));
+                    ew_tile_kernel<F><<<t.total_tiles, TILE_WARPS * 32, smem, dev->stream>>>(t, pc, pa, pb, tm_a, tm_b, ka, kb);
+                    after_launch(dev, "ew_tile_kernel");
+                    return;
+                }
             }
         }
     }

@@ -176,6 +176,10 @@ COPY_SHAPES = [
     ("rect narrow X batched ragged", (3, 20, 300), (0, 2, 1)),
     ("rect narrow Y batched ragged", (3, 300, 20), (0, 2, 1)),
     ("rect narrow Y=7 long X", (5000, 7), (1, 0)),
+    ("rect narrow X=3", (3, 1000), (1, 0)),
+    ("rect narrow X=31", (31, 333), (1, 0)),
+    ("rect narrow Y=32", (300, 32), (1, 0)),
+    ("rect narrow Y=4 batched", (2, 1500, 4), (0, 2, 1)),
 ]
 
 

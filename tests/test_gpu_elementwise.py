@@ -306,6 +306,8 @@ KERNEL_SHAPES = [
     ("rect tile a + b^T, narrow Y=24", (24, 900), None, "T"),
     ("rect tile batched, narrow X", (3, 310, 33), None, "T3"),
     ("rect tile batched, narrow Y", (3, 18, 333), None, "T3"),
+    ("rect tile a + b^T, narrow X=5", (1000, 5), None, "T"),
+    ("rect tile a + b^T, narrow Y=31", (31, 257), None, "T"),
 ]
 
 
