@@ -239,6 +239,11 @@ inline int tile_min_y(size_t esz) {
     static int v = [] { const char *e = getenv("RC_TILE_MIN_Y"); int x = e ? atoi(e) : 0; return x >= 2 ? x : 0; }();
     return v ? v : std::max<int>(2, (int)((48 + esz - 1) / esz));
 }
+// rows per CTA of ew_rows_kernel when an operand is broadcast over the rows (RC_ROWS_PER_CTA, experiments; default 1)
+inline int ew_rows_per_cta() {
+    static const int v = [] { const char *e = getenv("RC_ROWS_PER_CTA"); int x = e ? atoi(e) : 1; return x >= 1 ? x : 1; }();
+    return v;
+}
 // RC_TILE_RECT=0 switches the rectangular-tile kernel off (experiments: the square kernel then takes those shapes)
 inline bool tile_rect_enabled() {
     static bool v = [] { const char *e = getenv("RC_TILE_RECT"); return !(e && e[0] == '0'); }();
@@ -797,6 +802,9 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
             if (c.ndim == 1) {
                 ew_kernel<F, V, 1><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
             } else if (c.ndim == 2 && c.shape[0] / V >= 512 && c.shape[1] < (1ll << 31) &&
+                       // a splat operand that changes from row to row stays on the flat kernel: the rows kernel would be
+                       // correct with one row per CTA, but its dependent scalar load at the head of every CTA measured slower
+                       // ((n,n)+(n,1) 6.76 -> 6.12 TB/s, outer sum (n,1)+(1,n) 4.38 -> 4.07 TB/s)
                        !(mode_a == MODE_SPLAT && c.stride[slot_a][1] != 0) &&
                        !(mode_b == MODE_SPLAT && c.stride[slot_b][1] != 0)) {
                 EwRowsDesc rd;
@@ -813,8 +821,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                 // rows per CTA when an operand is broadcast over the rows.  Measured on cfg1 (B200): R = 2 / 4 / 8 / 16 /
                 // 32 -> 6.72 / 6.63 / 6.46 / 6.29 / 6.12 TB/s: the re-read of the broadcast operand is served by L2 and
                 // costs less than the parallelism lost to longer CTAs, so the default is one row (one-shot grid).
-                static const int rows_knob = [] { const char *e = getenv("RC_ROWS_PER_CTA"); int x = e ? atoi(e) : 1; return x >= 1 ? x : 1; }();
-                rd.rows_per_cta = bcast ? rows_knob : 1;
+                rd.rows_per_cta = bcast ? ew_rows_per_cta() : 1;
                 uint32_t chunks = (rd.n0 + EW_BLOCK * EW_UNROLL - 1) / (EW_BLOCK * EW_UNROLL);
                 rd.div_chunks = FastDiv(chunks);
                 int64_t groups = (rd.n1 + rd.rows_per_cta - 1) / rd.rows_per_cta;

@@ -180,6 +180,8 @@ COPY_SHAPES = [
     ("rect narrow X=31", (31, 333), (1, 0)),
     ("rect narrow Y=32", (300, 32), (1, 0)),
     ("rect narrow Y=4 batched", (2, 1500, 4), (0, 2, 1)),
+    ("rect narrow Y=2", (100000, 2), (1, 0)),
+    ("rect narrow Y=3", (4097, 3), (1, 0)),
 ]
 
 

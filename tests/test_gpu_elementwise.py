@@ -339,6 +339,23 @@ def test_kernel_variants(dev, name, shape, amode, bmode, dtype):
         assert np.array_equal(tc.to_numpy(), view_np(c, lc), equal_nan=True), (name, op)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32])
+@pytest.mark.parametrize("shape", [(37, 4096), (300, 2048), (5, 1024 + 16)])
+def test_outer_sum_of_two_broadcast_operands(dev, dtype, shape):
+    """(n,1) + (1,m): one operand is a splat along the output's contiguous axis that changes from row to row, the other
+    is broadcast over the rows (orbital-energy denominators e_i + e_a are built this way); flat vector kernel."""
+    rng = np.random.default_rng(seed_of("outer", shape, np.dtype(dtype).name))
+    n, m = shape
+    col, row = rand_data(rng, n, dtype), rand_data(rng, m, dtype)
+    lcol, lrow = L.Layout(shape, (1, 0), 0), L.Layout(shape, (0, 1), 0)
+    for op in ("add", "sub", "mul"):
+        for (x, lx, y, ly) in ((col, lcol, row, lrow), (row, lrow, col, lcol)):
+            tc = rt.Tensor(upload(dev, x), P(lx)).binary(op, rt.Tensor(upload(dev, y), P(ly)))
+            c, lc = oracle.tensor_binary(op, x, lx, y, ly)
+            assert same(tc.layout, lc)
+            assert np.array_equal(tc.to_numpy(), view_np(c, lc)), (op, shape)
+
+
 def test_misaligned_views_fall_back_to_scalar_path(dev):
     rng = np.random.default_rng(3)
     a = rand_data(rng, 5000, np.float64)
