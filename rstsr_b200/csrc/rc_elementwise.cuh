@@ -831,7 +831,11 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                     after_launch(dev, "ew_rows_kernel");
                     return;
                 }
-                ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+                ew_kernel<F, V, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+            } else if (c.ndim == 2) {
+                // compile-time rank 2: the runtime-rank walk costs 98 instructions per pack on an outer sum (ncu:
+                // issue-active 78 % at 48 % DRAM, profiles/r01_ncu_outer_summary.json)
+                ew_kernel<F, V, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
             } else {
                 ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
             }
@@ -839,7 +843,8 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
             return;
         }
     }
-    ew_kernel<F, 1, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+    if (c.ndim == 2) ew_kernel<F, 1, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+    else ew_kernel<F, 1, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
     after_launch(dev, "ew_kernel");
 }
 
