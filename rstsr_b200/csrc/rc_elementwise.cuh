@@ -831,18 +831,18 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                     after_launch(dev, "ew_rows_kernel");
                     return;
                 }
-                ew_kernel<F, V, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
-            } else if (c.ndim == 2) {
-                // compile-time rank 2: the runtime-rank walk costs 98 instructions per pack on an outer sum (ncu:
-                // issue-active 78 % at 48 % DRAM, profiles/r01_ncu_outer_summary.json)
-                ew_kernel<F, V, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+                ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
             } else {
+                // (a compile-time rank-2 instance of the VECTOR kernel was measured too: outer sum unchanged at 4.4 TB/s,
+                // (n,n) + (n,1) 6.76 -> 6.51 TB/s -- profiles/r01_results/probe_ew_nd2_all.txt -- so packs keep the
+                // runtime-rank walk; the scalar path below is where rank 2 pays)
                 ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
             }
             after_launch(dev, "ew_kernel");
             return;
         }
     }
+    // scalar path: element-rate bound, so 2-D problems take the compile-time rank (f32 a[:, 1:-1] copy 3.8 -> 5.45 TB/s)
     if (c.ndim == 2) ew_kernel<F, 1, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
     else ew_kernel<F, 1, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
     after_launch(dev, "ew_kernel");
