@@ -106,14 +106,68 @@ class Tensor:
     def reverse_axes(self) -> "Tensor":
         return self.transpose(None)
 
-    def flip(self, axis: int) -> "Tensor":
-        return self[tuple(slice(None, None, -1) if i == (axis % self.ndim) else slice(None) for i in range(self.ndim))]
+    def flip(self, axes: Union[None, int, Sequence[int]] = None) -> "Tensor":
+        """rt::flip (manipulation/flip.rs:3-20): reverse the given axes (all of them for None); a view."""
+        if isinstance(axes, (int, np.integer)):
+            ax = [int(axes) % self.ndim] if -self.ndim <= axes < self.ndim else _normalize_axes([int(axes)], self.ndim)
+        elif axes is None:
+            ax = list(range(self.ndim))
+        else:
+            ax = _normalize_axes(axes, self.ndim)
+        return self[tuple(slice(None, None, -1) if i in ax else slice(None) for i in range(self.ndim))]
 
-    def expand_dims(self, axis: int) -> "Tensor":
+    def expand_dims(self, axes: Union[int, Sequence[int]]) -> "Tensor":
+        """rt::expand_dims / unsqueeze (manipulation/expand_dims.rs:3-20): the axes index the RESULT (ndim + len(axes)
+        dimensions), duplicates are an error, insertion runs in ascending order.  An inserted unit axis gets stride 1
+        (the reference's dim_insert copies a neighbour's stride; a unit axis is never stepped along)."""
         l = self.layout
-        if axis < 0:
-            axis += l.ndim + 1
-        return self._with(Layout(l.shape[:axis] + (1,) + l.shape[axis:], l.stride[:axis] + (1,) + l.stride[axis:], l.offset))
+        if isinstance(axes, (int, np.integer)):
+            axis = int(axes)
+            if not -(l.ndim + 1) <= axis <= l.ndim:
+                raise _ffi.RstsrCudaError(2, f"axis {axis} out of bounds for inserting into ndim {l.ndim}")
+            ins = [axis + l.ndim + 1 if axis < 0 else axis]
+        else:
+            ins = sorted(_normalize_axes(axes, l.ndim + len(list(axes))))
+        shape, stride = list(l.shape), list(l.stride)
+        for axis in ins:
+            shape.insert(axis, 1)
+            stride.insert(axis, 1)
+        return self._with(Layout(tuple(shape), tuple(stride), l.offset))
+
+    unsqueeze = expand_dims
+
+    def squeeze(self, axes: Union[None, int, Sequence[int]] = None) -> "Tensor":
+        """rt::squeeze (manipulation/squeeze.rs:3-38): drop the given unit axes (every unit axis for None); an axis
+        of another extent and repeated axes are InvalidValue errors (dim_eliminate, indexer.rs:256-267)."""
+        l = self.layout
+        if axes is None:
+            drop = [i for i in range(l.ndim) if l.shape[i] == 1]
+        else:
+            raw = [int(axes)] if isinstance(axes, (int, np.integer)) else [int(a) for a in axes]
+            drop = [a + l.ndim if a < 0 else a for a in raw]
+            if any(a < 0 for a in drop):
+                raise _ffi.RstsrCudaError(2, "Some negative index is too small.")
+            if len(set(drop)) != len(drop):
+                raise _ffi.RstsrCudaError(2, "Same axes is not allowed here.")
+            for a in drop:
+                if a >= l.ndim:
+                    raise _ffi.RstsrCudaError(2, f"axis {a} out of bounds for ndim {l.ndim}")
+                if l.shape[a] != 1:
+                    raise _ffi.RstsrCudaError(2, "Dimension to be eliminated is not 1.")
+        keep = [i for i in range(l.ndim) if i not in drop]
+        return self._with(Layout(tuple(l.shape[i] for i in keep), tuple(l.stride[i] for i in keep), l.offset))
+
+    def moveaxis(self, source: Union[int, Sequence[int]], destination: Union[int, Sequence[int]]) -> "Tensor":
+        """rt::moveaxis (manipulation/moveaxis.rs:3-36): NumPy's rule -- the axes not named keep their order, each
+        source axis is inserted at its destination, destinations taken in ascending order."""
+        src = _normalize_axes([source] if isinstance(source, (int, np.integer)) else source, self.ndim)
+        dst = _normalize_axes([destination] if isinstance(destination, (int, np.integer)) else destination, self.ndim)
+        if len(src) != len(dst):
+            raise _ffi.RstsrCudaError(2, "`source` and `destination` arguments must have the same number of elements")
+        order = [i for i in range(self.ndim) if i not in src]
+        for d, s_ in sorted(zip(dst, src)):
+            order.insert(d, s_)
+        return self.transpose(order)
 
     def broadcast_to(self, shape: Sequence[int]) -> "Tensor":
         target = Layout.contig(shape, self.device.default_order())
@@ -533,6 +587,19 @@ def allclose(a: Tensor, b: Tensor, rtol: float = 1.0e-5, atol: float = 1.0e-8, e
 
 
 # ---- creation from tensors: compositions of OpAssignAPI (rstsr-core/src/tensor/creation_from_tensor.rs) ----
+def _normalize_axes(axes: Sequence[int], ndim: int) -> list:
+    """normalize_axes_index(allow_duplicate = false) (rstsr-common/src/axis_index.rs:379-412), order kept."""
+    out = []
+    for a in axes:
+        a = int(a)
+        if not -ndim <= a < ndim:
+            raise _ffi.RstsrCudaError(2, f"axis {a} out of bounds for ndim {ndim}")
+        out.append(a + ndim if a < 0 else a)
+    if len(set(out)) != len(out):
+        raise _ffi.RstsrCudaError(2, "Duplicate axes are not allowed.")
+    return out
+
+
 def _check_axis(axis: int, ndim: int) -> int:
     if not -ndim <= axis < ndim:
         raise _ffi.RstsrCudaError(2, f"axis {axis} out of bounds for ndim {ndim}")
