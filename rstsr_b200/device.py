@@ -116,6 +116,17 @@ def broadcast_layout(la: Layout, lb: Layout, order: int) -> Tuple[Layout, Layout
     return Layout.from_c(oa), Layout.from_c(ob)
 
 
+def broadcast_shapes(shapes: Sequence[Sequence[int]], order: int = _ffi.ROW_MAJOR) -> Tuple[int, ...]:
+    """rt::broadcast_shapes (rstsr-core/src/tensor/manipulation/broadcast.rs; rule of rstsr-common/src/layout/
+    broadcast.rs:21-68): fold the shapes pairwise through the library's broadcast (right-aligned for RowMajor,
+    left-aligned for ColMajor)."""
+    out = Layout.contig((), order)
+    for shape in shapes:
+        out, _ = broadcast_layout(out, Layout.contig(tuple(int(d) for d in shape), order), order)
+        out = Layout.contig(out.shape, order)
+    return out.shape
+
+
 def layout_for_binary_op(la: Layout, lb: Layout, order: int) -> Layout:
     out = CLayout()
     check(_ffi.lib().rc_layout_for_binary_op(byref(la.to_c()), byref(lb.to_c()), order, byref(out)))

@@ -1,6 +1,6 @@
-"""View manipulations of the Python mirror that never reach the GPU (layouts only, no device needed): the bodies of the
-reference's NumPy-derived conformance tests rstsr-core/tests/core_func/manipulation/test_{expand_dims,squeeze,moveaxis,
-flip}.rs, plus a seeded cross-check of every view against NumPy on an index array."""
+"""View manipulations and shape broadcasting of the Python mirror that never reach the GPU (layouts only, no device
+needed): the bodies of the reference's NumPy-derived conformance tests rstsr-core/tests/core_func/manipulation/test_{expand_dims,
+squeeze,moveaxis,flip,broadcast_shapes}.rs, plus a seeded cross-check of every view against NumPy on an index array."""
 import itertools
 
 import numpy as np
@@ -188,3 +188,51 @@ def test_moveaxis_all_pairs_match_numpy():
     t, ref = view(shape), np.arange(n).reshape(shape)
     for s, d in itertools.product(range(-4, 4), repeat=2):
         assert np.array_equal(realise(t.moveaxis(s, d), n), np.moveaxis(ref, s, d))
+
+
+# ---- test_broadcast_shapes.rs (through the library's host algebra, rc_layout_broadcast, and the oracle) ----
+BROADCAST_OK = [
+    ([], ()), ([()], ()), ([(7,)], (7,)), ([(1, 2), (2,)], (1, 2)), ([(1, 1)], (1, 1)), ([(1, 1), (3, 4)], (3, 4)),
+    ([(6, 7), (5, 6, 1), (7,), (5, 1, 7)], (5, 6, 7)), ([(5, 6, 1)], (5, 6, 1)), ([(1, 3), (3, 1)], (3, 3)),
+    ([(1, 0), (0, 0)], (0, 0)), ([(0, 1), (0, 0)], (0, 0)), ([(1, 0), (0, 1)], (0, 0)), ([(1, 1), (0, 0)], (0, 0)),
+    ([(1, 1), (1, 0)], (1, 0)), ([(1, 1), (0, 1)], (0, 1)), ([(), (0,)], (0,)), ([(0,), (0, 0)], (0, 0)),
+    ([(0,), (0, 1)], (0, 0)), ([(1,), (0, 0)], (0, 0)), ([(), (0, 0)], (0, 0)), ([(1, 1), (0,)], (1, 0)),
+    ([(1,), (0, 1)], (0, 1)), ([(1,), (1, 0)], (1, 0)), ([(), (1, 0)], (1, 0)), ([(), (0, 1)], (0, 1)),
+    ([(1,), (3,)], (3,)), ([(2,), (3, 2)], (3, 2)),
+    ([(1, 2)] * 32, (1, 2)), ([(1, 2)] * 100, (1, 2)), ([(2,)] * 32 + [()], (2,)),
+]
+BROADCAST_BAD = [[(3,), (4,)], [(2, 3), (2,)], [(3,), (3,), (4,)], [(1, 3, 4), (2, 3, 3)],
+                 [(1, 2), (3, 1), (3, 2), (10, 5)], [(2,), (2, 3)], [(2,)] * 32 + [(3,)]]
+
+
+def _oracle_broadcast_shapes(shapes, order):
+    from oracle import layout as OL
+    out = ()
+    for s in shapes:
+        out = tuple(OL.broadcast_shape(out, tuple(s), order)[0])
+    return out
+
+
+def test_broadcast_shapes_row_major():
+    from oracle import layout as OL
+    for shapes, want in BROADCAST_OK:
+        assert rt.broadcast_shapes(shapes, rt.ROW_MAJOR) == want, shapes
+        assert _oracle_broadcast_shapes(shapes, OL.ROW_MAJOR) == want, shapes
+        if all(len(s) for s in shapes):  # NumPy agrees (row-major rule)
+            assert np.broadcast_shapes(*shapes) == want
+    for shapes in BROADCAST_BAD:
+        assert err_kind(lambda: rt.broadcast_shapes(shapes, rt.ROW_MAJOR)) == "InvalidLayout"
+        with pytest.raises(OL.LayoutError):
+            _oracle_broadcast_shapes(shapes, OL.ROW_MAJOR)
+
+
+def test_broadcast_shapes_col_major():
+    """left-aligned rule of a column-major device (broadcast.rs:34-37)"""
+    from oracle import layout as OL
+    for shapes, want in (([(1, 6, 1, 8), (5, 1, 7)], (5, 6, 7, 8)), ([(4, 5), (4,)], (4, 5)),
+                         ([(5, 3, 15), (5, 1, 15)], (5, 3, 15)), ([(5, 3, 15), (5, 3)], (5, 3, 15))):
+        assert rt.broadcast_shapes(shapes, rt.COL_MAJOR) == want
+        assert _oracle_broadcast_shapes(shapes, OL.COL_MAJOR) == want
+    assert err_kind(lambda: rt.broadcast_shapes([(3,), (2, 1)], rt.COL_MAJOR)) == "InvalidLayout"
+    with pytest.raises(OL.LayoutError):
+        _oracle_broadcast_shapes([(3,), (2, 1)], OL.COL_MAJOR)
