@@ -97,6 +97,7 @@ class Tensor:
     permute_dims = transpose
 
     def swapaxes(self, a1: int, a2: int) -> "Tensor":
+        a1, a2 = _check_axis(a1, self.ndim), _check_axis(a2, self.ndim)  # out of range: InvalidValue, as in the reference
         ax = list(range(self.ndim))
         ax[a1], ax[a2] = ax[a2], ax[a1]
         return self.transpose(ax)

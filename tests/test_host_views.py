@@ -236,3 +236,26 @@ def test_broadcast_shapes_col_major():
     assert err_kind(lambda: rt.broadcast_shapes([(3,), (2, 1)], rt.COL_MAJOR)) == "InvalidLayout"
     with pytest.raises(OL.LayoutError):
         _oracle_broadcast_shapes([(3,), (2, 1)], OL.COL_MAJOR)
+
+
+# ---- test_transpose.rs ----
+def test_transpose_and_swapaxes_kats():
+    a = view((2, 2))
+    assert np.array_equal(realise(a.transpose(), 4), np.arange(4).reshape(2, 2).T)
+    for bad in ([0], [0, 0], [0, 1, 2]):
+        err_kind(lambda: a.transpose(bad))
+    arr = view((2, 3))
+    want = np.arange(6).reshape(2, 3).T
+    assert np.array_equal(realise(arr.transpose([1, 0]), 6), want)
+    assert np.array_equal(realise(arr.transpose([-1, -2]), 6), want)
+    # swapaxes: every pair of axes (negative ones too) is a view of the same buffer with NumPy's shape and elements
+    shape = (3, 4, 5, 6)
+    n = int(np.prod(shape))
+    src, t = np.arange(n).reshape(shape), view(shape)
+    for bad in ((-5, 0), (4, 0), (0, -5), (0, 4)):
+        assert err_kind(lambda: t.swapaxes(*bad)) == "InvalidValue"
+    for i in range(-4, 4):
+        for j in range(-4, 4):
+            c = t.swapaxes(i, j)
+            assert c.layout.offset == 0 and not c.owned
+            assert np.array_equal(realise(c, n), np.swapaxes(src, i, j))
