@@ -9,12 +9,18 @@ on the configurations of BASELINE.json (per GPU; weak scaling, every rank owns t
     cfg1   c = a + b            f64 (8192,8192) + (8192,)                     1,073,807,360 B
     cfg2   to_contig(RowMajor)  f64 (1024,1024,512) viewed transpose(2,0,1)   8,589,934,592 B   <- dominant kernel
     cfg3   sum over axis -1 and over axis 0 of f64 (16384,16384)             2 x 2,147,614,720 B
-At N > 1 the rows of cfg3 are sharded, so the axis-0 sum reduces the sharded axis: its (16384,) partial output
-is combined with an NCCL all-reduce inside the timed region (the one exchange step of this path).
+At N > 1 the rows of cfg3 are sharded, so the axis-0 sum reduces the sharded axis: rc_reduce_axes_sharded combines
+the (16384,) partials inside the timed region (the one exchange step of this path) and the combined result is
+checked against a torch all_reduce of the per-rank column sums.
 `value` = algorithmic bytes of all ranks / max-over-ranks device time, inputs resident in HBM.
+`per_config` = the other named configurations, measured in the same process with the same rules: cfg2 ColMajor,
+          cfg3 f32 / max, and the SHARDED configs strong-scaled over the N ranks: cfg4 (64,64,512,512) split on output
+          axis 0 and cfg5 2^33 f64 sum_all / max_all split evenly (collective and host scalar inside the timing);
+          every output is verified against torch on the same data.
 `e2e`   = same metric through the C ABI with HOST buffers: pinned host -> device copies of every input and
-          device -> host copies of every result inside the timed region.
-`--impl reference`: the reference's CPU path (C/OpenMP port in oracle/, all host threads) on a bounded sample.
+          device -> host copies of every result inside the timed region; next to it the bare copy ceiling of the
+          same bytes (plain cudaMemcpyAsync both ways at once from the same buffers, all ranks concurrently).
+`--impl reference`: the reference's CPU path (C/OpenMP port in oracle/, every host core) on the FULL step.
 """
 from __future__ import annotations
 
@@ -154,33 +160,60 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the C + OpenMP port of the DeviceFaer loops (oracle/), bounded sample
+# reference arm / cpu baseline: the C + OpenMP port of the DeviceFaer loops (oracle/), FULL step
 # ------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """CPUs this process may run on (the rayon global pool of DeviceFaer::default() sizes itself the same way)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cpus = list(range(os.cpu_count() or 1))
+    return cpus
+
+
+def _cpu_ranges(cpus):
+    out, i = [], 0
+    while i < len(cpus):
+        j = i
+        while j + 1 < len(cpus) and cpus[j + 1] == cpus[j] + 1:
+            j += 1
+        out.append(f"{cpus[i]}-{cpus[j]}" if j > i else f"{cpus[i]}")
+        i = j + 1
+    return ",".join(out)
+
+
 class CpuPort:
-    """Times the reference's CPU algorithm (rayon regimes restated with OpenMP, oracle/rstsr_oracle.c) on a
-    bounded sample of the step: 1/8 of every configuration along its outermost axis, so the mix of kernels is
-    the step's own (cfg1 (1024,8192)+(8192,); cfg2 (128,1024,512); cfg3 (2048,16384), both axes)."""
-    SAMPLE = "1/8 of each config along its outermost axis: cfg1 (1024,8192)+(8192,); cfg2 (128,1024,512); cfg3 (2048,16384) both axes"
+    """Times the reference's CPU algorithm (rayon regimes restated with OpenMP, oracle/rstsr_oracle.c) on the FULL step:
+    cfg1 (8192,8192)+(8192,); cfg2 (1024,1024,512) permuted copy; cfg3 (16384,16384) both axes -- the same shapes,
+    dtypes and byte counts as the GPU arm (13.96 GB of algorithmic traffic, about a second per step on a 2-socket box).
+    Thread count = every CPU in the process's affinity mask, set EXPLICITLY: torchrun exports OMP_NUM_THREADS=1.
+    Conservative for the reference: the OpenMP port uses a static `omp for` where rayon spawns nested per-element
+    tasks for runs >= 4096 (cpu_rayon/op_with_func.rs:57-67), so the real DeviceFaer is not faster than this."""
+    SAMPLE = "full step: cfg1 (8192,8192)+(8192,); cfg2 (1024,1024,512) permuted copy; cfg3 (16384,16384) sum axis -1 and 0"
 
     def __init__(self):
+        import ctypes
         import numpy as np
         import oracle
         from oracle import layout as OL
         self.np, self.oracle, self.OL = np, oracle, OL
         self.lib = oracle.load(native=True)  # -march=native build on the box that runs it
-        self.lib.orc_num_threads.restype = __import__("ctypes").c_int
+        self.lib.orc_num_threads.restype = ctypes.c_int
+        self.cpus = host_cores()
+        try:
+            self.lib.orc_set_num_threads.argtypes = [ctypes.c_int]
+            self.lib.orc_set_num_threads(len(self.cpus))
+        except AttributeError:
+            pass
         self.cores = int(self.lib.orc_num_threads())
         rng = np.random.default_rng(42)
-        self.r1 = N1 // 8
-        self.a1 = rng.random(self.r1 * N1)
+        self.a1 = rng.random(N1 * N1)
         self.b1 = rng.random(N1)
-        self.c1 = np.empty(self.r1 * N1)
-        self.s2 = (SHP2[0] // 8, SHP2[1], SHP2[2])
-        self.src2 = rng.random(self.s2[0] * self.s2[1] * self.s2[2])
+        self.c1 = np.empty(N1 * N1)
+        self.src2 = rng.random(SHP2[0] * SHP2[1] * SHP2[2])
         self.dst2 = np.empty_like(self.src2)
-        self.r3 = N3 // 8
-        self.m3 = rng.random(self.r3 * N3)
-        self.bytes = (2 * self.a1.size * 8 + N1 * 8) + 2 * self.src2.size * 8 + 2 * (self.m3.size * 8 + N3 * 8)
+        self.m3 = rng.random(N3 * N3)
+        self.bytes = BYTES_STEP
         # first touch of every output page outside the timed region
         self.c1[:] = 0
         self.dst2[:] = 0
@@ -190,7 +223,7 @@ class CpuPort:
         np, oracle, OL = self.np, self.oracle, self.OL
         cl = oracle._cl
         # cfg1: translate_to_col_major(K) + with_contig -> run 8192, outer [8192]
-        la = OL.c_contig_layout([self.r1, N1])
+        la = OL.c_contig_layout([N1, N1])
         la_b, lb_b = OL.broadcast_layout(la, OL.c_contig_layout([N1]), "row")
         full = OL.translate_to_col_major([la, la_b, lb_b], "K")
         outer, run = OL.translate_to_col_major_with_contig(full)
@@ -199,34 +232,42 @@ class CpuPort:
                                  self.a1.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cl(use[1])),
                                  self.b1.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cl(use[2])), ctypes.c_int64(run))
         # cfg2: assign_arbitary, row-major device, strided source -> per-element two-odometer copy in parallel
-        lsrc = OL.c_contig_layout(self.s2).transpose([2, 0, 1])
+        lsrc = OL.c_contig_layout(SHP2).transpose([2, 0, 1])
         ldst = OL.c_contig_layout(lsrc.shape)
         oracle.assign_arbitary(self.dst2, ldst, self.src2, lsrc, "row", parallel=True, lib=self.lib)
         # cfg3: reduce_axes regimes (a) and (b)
-        l3 = OL.c_contig_layout([self.r3, N3])
+        l3 = OL.c_contig_layout([N3, N3])
         oracle.reduce_axes("sum", self.m3, l3, [-1], device="rayon", lib=self.lib)
         oracle.reduce_axes("sum", self.m3, l3, [0], device="rayon", lib=self.lib)
+
+    def describe(self, value):
+        return {"value": round(value, 2), "unit": UNIT, "cores": self.cores, "kind": "port", "sample": self.SAMPLE,
+                "affinity": _cpu_ranges(self.cpus), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+                "note": "conservative: static omp-for where rayon nests per-element tasks (op_with_func.rs:57-67)"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     port = CpuPort()
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         port.step()
+    # the whole run must end within a few minutes: at most `steps` steps and at most ~100 s of timed work
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    while done < args.steps and (done < 2 or time.perf_counter() - t0 < 100.0):
         port.step()
-    dt = (time.perf_counter() - t0) / args.steps
+        done += 1
+    dt = (time.perf_counter() - t0) / done
     v = port.bytes / dt / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+            "steps": done, "warmup": max(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": port.SAMPLE},
-            "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": port.cores, "kind": "port",
-                             "sample": port.SAMPLE},
+            "config": {"workload": WORKLOAD, "sample": port.SAMPLE, "bytes_per_step": BYTES_STEP},
+            "cpu_baseline": port.describe(v),
             "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "C/OpenMP port of the DeviceFaer loops (the Rust reference cannot be built: no rustc in the image)"}
+            "note": "C/OpenMP port of the DeviceFaer loops (the Rust reference cannot be built: no rustc in the image); "
+                    "one host, all its cores, whatever --gpus says"}
     emit(line)
 
 
@@ -250,13 +291,15 @@ def run_product(args, rank, local_rank, world):
     dev = rt.DeviceCuda(local_rank, rt.ROW_MAJOR, stream=stream)
 
     comm = None
+    peer_window = False
     if world > 1:
         uid = [rt.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = rt.Comm(dev, world, rank, uid[0])
+        peer_window = comm.info()[2]
 
-    def wrap(t):
-        return dev.wrap(t.data_ptr(), t.numel(), np.float64)
+    def wrap(t, dt=np.float64):
+        return dev.wrap(t.data_ptr(), t.numel(), dt)
 
     g = torch.Generator(device="cuda")
     g.manual_seed(42 + rank)
@@ -292,9 +335,10 @@ def run_product(args, rank, local_rank, world):
             fn()
 
     def axis0_sum():
-        dev.reduce_axes_into("sum", rm3, lm3, [0], roc, lo3)
-        if comm is not None:  # rows are sharded across ranks: combine the partial column sums
-            comm.all_reduce("sum", roc, N3)
+        if comm is None:
+            dev.reduce_axes_into("sum", rm3, lm3, [0], roc, lo3)
+        else:  # rows are sharded across ranks: local partial + cross-GPU combine in one entry point
+            comm.reduce_axes_sharded("sum", rm3, lm3, [0], N3 * world, roc, lo3)
 
     def step(record=False):
         timed("cfg1", lambda: dev.op_mutc_refa_refb("add", rc1, la1, ra1, la1, rb1, lb1), record)
@@ -330,18 +374,44 @@ def run_product(args, rank, local_rank, world):
     elapsed = float(elapsed.item())
     clk = clocks.stop() if clocks else None
 
-    # sanity of the timed results (outside the timed region)
+    # ---- the timed results are checked (outside the timed region) on EVERY rank ----
     assert torch.equal(c1.view(N1, N1), a1.view(N1, N1) + b1)
     probe = src2.view(*SHP2)[5:7].permute(2, 0, 1).contiguous()
     assert torch.equal(dst2.view(SHP2[2], SHP2[0], SHP2[1])[:, 5:7, :], probe)
     ref_r = m3.view(N3, N3).sum(dim=1)
     assert float(((o3r - ref_r).abs() / ref_r.abs()).max()) < 1e-12
+    ref_c = m3.view(N3, N3).sum(dim=0)
+    if dist is not None:  # the combined column sums: every rank must hold the all-reduced result
+        dist.all_reduce(ref_c)
+    assert float(((o3c - ref_c).abs() / ref_c.abs()).max()) < 1e-12, "axis-0 sum (combined over ranks) mismatch"
+    if dist is not None:  # ... and bitwise the same one on every rank (rank-ordered fold)
+        same = o3c.clone()
+        dist.broadcast(same, src=0)
+        if peer_window:
+            assert torch.equal(same, o3c), "combined result differs between ranks"
+    checks = {"cfg1": "bit-exact vs torch", "cfg2": "bit-exact vs torch (slab)", "cfg3_rows": "rel 1e-12 vs torch",
+              "cfg3_cols": ("rel 1e-12 vs torch all_reduce of the per-rank sums; bitwise equal on all ranks"
+                            if world > 1 else "rel 1e-12 vs torch")}
 
+    peak, peak_kind = measured_peak()
     per_op = {}
     for k, pairs in ev.items():
         ms = sum(e0.elapsed_time(e1) for e0, e1 in pairs) / max(len(pairs), 1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
         nbytes = {"cfg1": BYTES_CFG1, "cfg2": BYTES_CFG2, "cfg3_rows": BYTES_CFG3, "cfg3_cols": BYTES_CFG3}[k]
-        per_op[k] = {"us": round(ms * 1e3, 1), "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1)}
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        per_op[k] = {"us": round(ms * 1e3, 1), "gbs": round(gbs, 1), "frac_measured": round(gbs / peak, 4),
+                     "frac_8TBs": round(gbs / 8000, 4), "check": checks[k]}
+    del a1, b1, c1, src2, dst2, m3, o3r, o3c, probe, ref_r, ref_c
+
+    # ---- the other named configurations, same process, same rules ----
+    per_config = None
+    if not args.no_per_config:
+        per_config = run_per_config(args, rank, world, dev, comm, rt, np, torch, dist, peak)
+    torch.cuda.empty_cache()
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
     e2e = run_e2e(args, dev, rt, np, torch, dist, comm, world)
@@ -353,13 +423,14 @@ def run_product(args, rank, local_rank, world):
 
     if rank != 0:
         return
-    peak, peak_kind = measured_peak()
     value = world * BYTES_STEP * args.steps / elapsed / 1e9
     dom = per_op["cfg2"]
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("ew_tile_kernel_cfg2_bytes")
+            tj = json.load(f)
+        traffic = tj.get("ew_tile_kernel_cfg2_bytes")
+        traffic_src = tj.get("source")
     except Exception:
         pass
     line = {
@@ -367,15 +438,17 @@ def run_product(args, rank, local_rank, world):
         "warmup": max(args.warmup, 3), "ms_per_step": round(elapsed / args.steps * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": published_baseline(), "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (every array >= 1 GiB vs 126 MB L2)",
-                   "collective": "NCCL all-reduce of the (16384,) axis-0 partial at N>1" if world > 1 else "none",
+                   "collective": ("rc_reduce_axes_sharded: " + ("one-kernel NVLink peer-window combine" if peer_window else
+                                  "ncclAllReduce") + " of the (16384,) axis-0 partial") if world > 1 else "none",
                    "bytes_per_step_per_gpu": BYTES_STEP},
         "pct_of_8TBs": round(value / world / 8000 * 100, 1),
         "pct_of_measured_peak": round(value / world / peak * 100, 1),
         "per_op": per_op,
+        "per_config": per_config,
         "roofline": {"bound": "hbm", "kernel": "ew_tile_kernel<FIdentity<u64>> (cfg2 permuted copy)",
                      "achieved": dom["gbs"], "peak": peak, "peak_kind": peak_kind + " (burst copy, MEASURED_PEAKS.json)",
                      "unit": "GB/s", "frac": round(dom["gbs"] / peak, 4), "traffic": traffic,
-                     "algorithmic_bytes": BYTES_CFG2},
+                     "traffic_source": traffic_src, "algorithmic_bytes": BYTES_CFG2},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -384,15 +457,164 @@ def run_product(args, rank, local_rank, world):
             port.step()
             t = time.perf_counter()
             reps = 0
-            while reps < 2 or (time.perf_counter() - t < 8 and reps < 20):
+            while reps < 2 or (time.perf_counter() - t < 10 and reps < 20):
                 port.step()
                 reps += 1
             dt = (time.perf_counter() - t) / reps
-            line["cpu_baseline"] = {"value": round(port.bytes / dt / 1e9, 2), "unit": UNIT, "cores": port.cores,
-                                    "kind": "port", "sample": port.SAMPLE}
+            line["cpu_baseline"] = port.describe(port.bytes / dt / 1e9)
         except Exception as exc:  # the checker is test infrastructure: its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
     emit(line)
+
+
+def run_per_config(args, rank, world, dev, comm, rt, np, torch, dist, peak):
+    """cfg2 ColMajor and the six remaining cfg3 cases (weak: every rank the full named shape), cfg4 and cfg5
+    STRONG-scaled over the ranks (the named total split evenly).  CUDA events on the launching stream, >= 3 warm-ups,
+    max over ranks, working sets far above L2; every output verified against torch on the same data."""
+    from rstsr_b200 import Layout
+    rows = {}
+    iters = max(3, min(args.steps, 10))
+
+    def wrap(t, dt=np.float64):
+        return dev.wrap(t.data_ptr(), t.numel(), dt)
+
+    def timeit(fn, n=iters, warmup=3):
+        for _ in range(warmup):
+            fn()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n * 1e-3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def report(name, total_bytes, sec, scaling, check):
+        gbs = total_bytes / sec / 1e9
+        rows[name] = {"scaling": scaling, "us": round(sec * 1e6, 1), "gbs_total": round(gbs, 1),
+                      "gbs_per_gpu": round(gbs / world, 1), "frac_measured": round(gbs / world / peak, 4),
+                      "frac_8TBs": round(gbs / world / 8000, 4), "bytes_total": int(total_bytes), "check": check}
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4242 + rank)
+    f64 = dict(dtype=torch.float64, device="cuda")
+
+    # ---- cfg2, ColMajor target (inner axis contiguous on both sides: vectorised copy, no transpose tile) ----
+    N = SHP2[0] * SHP2[1] * SHP2[2]
+    src = torch.rand(N, generator=g, **f64)
+    dst = torch.empty(N, **f64)
+    lsrc = Layout((SHP2[2], SHP2[0], SHP2[1]), (1, SHP2[1] * SHP2[2], SHP2[2]))
+    ldst = Layout.contig(lsrc.shape, rt.COL_MAJOR)
+    rs, rd = wrap(src), wrap(dst)
+    sec = timeit(lambda: dev.assign_arbitary(rd, ldst, rs, lsrc))
+    # F-contiguous (512,1024,1024) == C-contiguous (1024,1024,512) of the axes reversed
+    want = src.view(*SHP2)[3:5].permute(2, 0, 1)          # [k, i, j] for i in 3:5
+    got = dst.view(SHP2[1], SHP2[0], SHP2[2])[:, 3:5, :]  # memory [j][i][k]
+    assert torch.equal(got.permute(2, 1, 0), want), "cfg2 ColMajor mismatch"
+    report("cfg2_colmajor f64 to_contig(ColMajor) of (1024,1024,512).transpose(2,0,1)", world * 2 * N * 8, sec, "weak",
+           "bit-exact vs torch (slab)")
+    del src, dst, want, got
+
+    # ---- cfg3: f32 sum / max and f64 max, both axes (f64 sum is the headline step) ----
+    for dt, npdt, ops in ((torch.float32, np.float32, ("sum", "max")), (torch.float64, np.float64, ("max",))):
+        m = torch.rand(N3 * N3, generator=g, dtype=dt, device="cuda")
+        o = torch.empty(N3, dtype=dt, device="cuda")
+        rm, ro = wrap(m, npdt), wrap(o, npdt)
+        lm, lo = Layout((N3, N3), (N3, 1)), Layout((N3,), (1,))
+        es = m.element_size()
+        for op in ops:
+            for axis in (0, -1):
+                sec = timeit(lambda: dev.reduce_axes_into(op, rm, lm, [axis], ro, lo))
+                ref = getattr(m.view(N3, N3), op)(dim=axis)
+                ref = ref.values if op == "max" else ref
+                if op == "max":
+                    assert torch.equal(o, ref), f"cfg3 {dt} max axis {axis} mismatch"
+                    chk = "bit-exact vs torch"
+                else:  # f32 sums: tolerance 1e-5 relative (north star), both sides accumulate in f32
+                    assert float(((o - ref).abs() / ref.abs()).max()) < 1e-5, f"cfg3 f32 sum axis {axis} mismatch"
+                    chk = "rel 1e-5 vs torch"
+                report(f"cfg3 {str(dt)[6:]} {op} axis {axis} (16384,16384)", world * (N3 * N3 * es + N3 * es), sec, "weak", chk)
+        del m, o, ref
+
+    # ---- cfg4: strong scaling, sharded on output axis 0: rank r owns a_r, c_r = (64/g,64,512,512) C-contiguous and
+    #      b_r = its local C-contiguous (64, 64/g, 512, 512) block viewed permuted (1,0,3,2) (SURVEY 8d) ----
+    D0, D1, D2, D3 = 64, 64, 512, 512
+    if D0 % world == 0:
+        ni = D0 // world
+        loc = ni * D1 * D2 * D3
+        a = torch.rand(loc, generator=g, **f64)
+        bl = torch.rand(loc, generator=g, **f64)
+        c = torch.empty(loc, **f64)
+        ra, rb, rc = wrap(a), wrap(bl), wrap(c)
+        lc = Layout.contig((ni, D1, D2, D3), rt.ROW_MAJOR)
+        lbp = Layout((ni, D1, D2, D3), (D2 * D3, ni * D2 * D3, 1, D3))
+        sec = timeit(lambda: dev.op_mutc_refa_refb("add", rc, lc, ra, lc, rb, lbp), n=max(3, iters // 2))
+        bview = bl.view(D1, ni, D2, D3).permute(1, 0, 3, 2)
+        for j in (0, D1 // 2 + 1, D1 - 1):
+            assert torch.equal(c.view(ni, D1, D2, D3)[:, j], a.view(ni, D1, D2, D3)[:, j] + bview[:, j]), "cfg4 mismatch"
+        report("cfg4 f64 c = a + b.transpose(1,0,3,2) (64,64,512,512), axis 0 sharded", 3 * D0 * D1 * D2 * D3 * 8, sec,
+               "strong", "bit-exact vs torch (3 slabs per rank)")
+        v = torch.rand(D2 * D3, generator=g, **f64)
+        rv = wrap(v)
+        lv = Layout((ni, D1, D2, D3), (0, 0, D3, 1))
+        sec = timeit(lambda: dev.op_mutc_refa_refb("mul", rc, lc, ra, lc, rv, lv), n=max(3, iters // 2))
+        assert torch.equal(c.view(ni, D1, D2 * D3)[ni - 1], a.view(ni, D1, D2 * D3)[ni - 1] * v), "cfg4b mismatch"
+        report("cfg4b f64 c = a * v, v broadcast (0,0,512,1), axis 0 sharded", 2 * D0 * D1 * D2 * D3 * 8 + world * D2 * D3 * 8,
+               sec, "strong", "bit-exact vs torch (slab)")
+        del a, bl, c, v, bview
+
+    # ---- cfg5: 2^33 f64 (64 GiB) split evenly; per-GPU partial + cross-GPU combine + host scalar, all timed ----
+    total = 1 << 33
+    free_b, _ = torch.cuda.mem_get_info()
+    per = total // world
+    if per * 8 + (8 << 30) <= free_b:
+        x = torch.rand(per, generator=g, **f64)
+        # a planted maximum on one rank makes the max check meaningful
+        if rank == world - 1:
+            x[per // 3] = 1.5
+        rx = wrap(x)
+        lx = Layout((per,), (1,))
+        for op in ("sum", "max"):
+            if comm is None:
+                fn = lambda: dev.reduce_all(op, rx, lx)
+            else:
+                fn = lambda: comm.reduce_all_sharded(op, rx, lx, total)
+            sec = timeit(fn, n=max(3, iters // 2))
+            got = fn()
+            if op == "sum":
+                ref = torch.stack([x.view(1 << 10, -1).sum(dim=1).sum()])
+                if dist is not None:
+                    dist.all_reduce(ref)
+                assert abs(got - float(ref.item())) <= 1e-12 * abs(float(ref.item())), "cfg5 sum_all mismatch"
+                chk = "rel 1e-12 vs torch" + (" all_reduce" if world > 1 else "")
+            else:
+                ref = torch.stack([x.max()])
+                if dist is not None:
+                    dist.all_reduce(ref, op=dist.ReduceOp.MAX)
+                assert got == float(ref.item()) == 1.5, "cfg5 max_all mismatch"
+                chk = "bit-exact vs torch" + (" all_reduce(MAX)" if world > 1 else "")
+            report(f"cfg5 f64 {op}_all of 2^33 elements (64 GiB) split over the ranks, incl. combine + host scalar",
+                   total * 8, sec, "strong", chk)
+        del x
+    else:
+        rows["cfg5"] = {"skipped": f"{per * 8 >> 30} GiB per rank does not fit the free {free_b >> 30} GiB"}
+    return rows
+
+
+def pinned_alloc(rt, torch, numel, node):
+    """float64 torch view of a pinned staging buffer placed on NUMA node `node` (rc_host_alloc_on_node)."""
+    import ctypes
+    ptr, bound = rt.DeviceCuda.host_alloc(numel * 8, node)
+    buf = (ctypes.c_double * numel).from_address(ptr)
+    t = torch.frombuffer(buf, dtype=torch.float64, count=numel)
+    return t, ptr, bound
 
 
 def run_e2e(args, dev, rt, np, torch, dist, comm, world):
@@ -400,7 +622,9 @@ def run_e2e(args, dev, rt, np, torch, dist, comm, world):
     is copied back, all inside the timed region.  Three handles of the same GPU (upload / compute / download
     streams, ordered with rc_device_wait) pipeline the step in chunks along each config's outermost axis, so
     PCIe uploads, kernels and PCIe downloads overlap (full-duplex link): the step costs ~max(H2D, D2H) instead
-    of their sum.  Timed with CUDA events on the stream `dev` is bound to; the pipeline is fenced against it."""
+    of their sum.  Timed with CUDA events on the stream `dev` is bound to; the pipeline is fenced against it.
+    The staging buffers live on the GPU's own NUMA node (rc_host_alloc_on_node).  `ceiling` = the same bytes moved
+    by bare cudaMemcpyAsync both ways at once, all ranks concurrently: what the host links allow at this N."""
     from rstsr_b200 import Layout
     steps = max(1, min(args.steps, 3))
     up = rt.DeviceCuda(dev.ordinal, rt.ROW_MAJOR)
@@ -411,11 +635,21 @@ def run_e2e(args, dev, rt, np, torch, dist, comm, world):
         uid = [rt.Comm.unique_id() if dist.get_rank() == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ccomm = rt.Comm(cp, world, dist.get_rank(), uid[0])
-    pin = dict(dtype=torch.float64, pin_memory=True)
+    node = dev.numa_node() if not args.no_numa else -1
     n2 = SHP2[0] * SHP2[1] * SHP2[2]
-    h_a1 = torch.rand(N1 * N1, **pin); h_b1 = torch.rand(N1, **pin); h_c1 = torch.empty(N1 * N1, **pin)
-    h_s2 = torch.rand(n2, **pin); h_d2 = torch.empty(n2, **pin)
-    h_m3 = torch.rand(N3 * N3, **pin); h_or = torch.empty(N3, **pin); h_oc = torch.empty(N3, **pin)
+    ptrs, bounds = [], []
+
+    def pin(numel, fill):
+        t, ptr, bound = pinned_alloc(rt, torch, numel, node)
+        ptrs.append(ptr)
+        bounds.append(bound)
+        if fill:
+            t.copy_(torch.rand(numel, dtype=torch.float64))
+        return t
+
+    h_a1 = pin(N1 * N1, True); h_b1 = pin(N1, True); h_c1 = pin(N1 * N1, False)
+    h_s2 = pin(n2, True); h_d2 = pin(n2, False)
+    h_m3 = pin(N3 * N3, True); h_or = pin(N3, False); h_oc = pin(N3, False)
     d_a1 = cp.uninit_impl(np.float64, N1 * N1); d_b1 = cp.uninit_impl(np.float64, N1)
     d_c1 = cp.uninit_impl(np.float64, N1 * N1)
     d_s2 = cp.uninit_impl(np.float64, n2); d_d2 = cp.uninit_impl(np.float64, n2)
@@ -457,9 +691,10 @@ def run_e2e(args, dev, rt, np, torch, dist, comm, world):
             up.h2d_async(d_m3, h_m3.data_ptr() + k * r * N3 * 8, r * N3 * 8, k * r * N3 * 8)
         cp.wait(up)
         cp.reduce_axes_into("sum", d_m3, lm3, [-1], d_or, lo3)
-        cp.reduce_axes_into("sum", d_m3, lm3, [0], d_oc, lo3)
-        if ccomm is not None:
-            ccomm.all_reduce("sum", d_oc, N3)
+        if ccomm is None:
+            cp.reduce_axes_into("sum", d_m3, lm3, [0], d_oc, lo3)
+        else:
+            ccomm.reduce_axes_sharded("sum", d_m3, lm3, [0], N3 * world, d_oc, lo3)
         dn.wait(cp)
         dn.d2h_async(h_or.data_ptr(), d_or, N3 * 8)
         dn.d2h_async(h_oc.data_ptr(), d_oc, N3 * 8)
@@ -472,40 +707,71 @@ def run_e2e(args, dev, rt, np, torch, dist, comm, world):
         for h in (up, cp, dn):
             dev.wait(h)
 
+    def timed_region(body, reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fence_start()
+        for _ in range(reps):
+            body()
+        fence_end()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return float(sec.item())
+
     fence_start(); step(); fence_end()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fence_start()
-    for _ in range(steps):
-        step()
-    fence_end()
-    e1.record()
-    torch.cuda.synchronize()
-    sec = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-    sec = float(sec.item())
+    sec = timed_region(step, steps)
     # the host results are the real thing
     assert torch.equal(h_c1.view(N1, N1), h_a1.view(N1, N1) + h_b1)
     want = h_s2.view(*SHP2)[700:702].permute(2, 0, 1).contiguous()
     assert torch.equal(h_d2.view(SHP2[2], SHP2[0], SHP2[1])[:, 700:702, :], want)
     ref_r = h_m3.view(N3, N3).sum(dim=1)
     assert float(((h_or - ref_r).abs() / ref_r.abs()).max()) < 1e-12
-    if ccomm is None:
-        ref_c = h_m3.view(N3, N3).sum(dim=0)
-        assert float(((h_oc - ref_c).abs() / ref_c.abs()).max()) < 1e-12
+    ref_c = h_m3.view(N3, N3).sum(dim=0)
+    if dist is not None:  # gloo is not initialised: combine the reference through the GPU
+        ref_c_d = ref_c.cuda()
+        dist.all_reduce(ref_c_d)
+        ref_c = ref_c_d.cpu()
+    assert float(((h_oc - ref_c).abs() / ref_c.abs()).max()) < 1e-12, "e2e axis-0 sum (combined over ranks) mismatch"
     h2d_bytes = (h_a1.numel() + h_b1.numel() + h_s2.numel() + h_m3.numel()) * 8
     d2h_bytes = (h_c1.numel() + h_d2.numel() + h_or.numel() + h_oc.numel()) * 8
+
+    # ---- bare ceiling of the host links: the same bytes, plain copies, both directions at once ----
+    def bare():
+        up.wait(dn)
+        up.h2d_async(d_a1, h_a1.data_ptr(), N1 * N1 * 8)
+        up.h2d_async(d_s2, h_s2.data_ptr(), n2 * 8)
+        up.h2d_async(d_m3, h_m3.data_ptr(), N3 * N3 * 8)
+        dn.d2h_async(h_c1.data_ptr(), d_c1, N1 * N1 * 8)
+        dn.d2h_async(h_d2.data_ptr(), d_d2, n2 * 8)
+
+    fence_start(); bare(); fence_end()
+    sec_bare = timed_region(bare, 2) / 2
     if ccomm is not None:
         ccomm.close()
+    del d_a1, d_b1, d_c1, d_s2, d_d2, d_m3, d_or, d_oc
+    cp.synchronize()
+    del h_a1, h_b1, h_c1, h_s2, h_d2, h_m3, h_or, h_oc, want, ref_r, ref_c
+    for ptr in ptrs:
+        rt.DeviceCuda.host_free(ptr)
+    ms = sec / steps * 1e3
     return {"value": round(world * BYTES_STEP * steps / sec / 1e9, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-            "d2h_bytes_per_step": d2h_bytes, "steps": steps, "ms_per_step": round(sec / steps * 1e3, 2),
+            "d2h_bytes_per_step": d2h_bytes, "steps": steps, "ms_per_step": round(ms, 2),
+            "ceiling": {"ms_per_step": round(sec_bare * 1e3, 2),
+                        "h2d_gbs_per_gpu": round(h2d_bytes / sec_bare / 1e9, 1),
+                        "d2h_gbs_per_gpu": round(d2h_bytes / sec_bare / 1e9, 1),
+                        "what": "bare cudaMemcpyAsync of the step's bytes, H2D and D2H concurrently, all ranks at once"},
+            "frac_of_ceiling": round(sec_bare * 1e3 / ms, 3),
+            "numa": {"gpu_node": node, "placement": {0: "none", 1: "mbind", 2: "first-touch"}.get(max(bounds) if bounds else 0)},
+            "check": "host outputs: cfg1 / cfg2 bit-exact, cfg3 rel 1e-12 (axis 0 vs the all-reduced reference at N>1)",
             "path": "pinned host -> rc_memcpy_h2d_async -> rc_op_mutc_refa_refb / rc_assign_arbitary / "
-                    "rc_reduce_axes_into -> rc_memcpy(2d)_d2h_async -> pinned host; upload/compute/download handles "
-                    "ordered by rc_device_wait, chunked 4/16/4"}
+                    "rc_reduce_axes_into / rc_reduce_axes_sharded -> rc_memcpy(2d)_d2h_async -> pinned host; "
+                    "upload/compute/download handles ordered by rc_device_wait, chunked 4/16/4"}
 
 
 _SAVED_STDOUT = None
@@ -534,6 +800,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the per_config block (cfg2 ColMajor, cfg3 f32/max, cfg4, cfg5)")
+    ap.add_argument("--no-numa", action="store_true", help="e2e staging buffers without NUMA placement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

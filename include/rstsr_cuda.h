@@ -182,7 +182,12 @@ int rc_device_create_on_stream(int ordinal, rc_order default_order, void *cuda_s
 int rc_device_destroy(rc_device *dev);
 int rc_device_default_order(const rc_device *dev, rc_order *out);
 int rc_device_set_default_order(rc_device *dev, rc_order order);
-int rc_device_same_device(const rc_device *a, const rc_device *b, int *same); /* ordinal & order equal */
+/* same GPU, same default order AND same stream: two handles with different streams are not ordered against each
+ * other, so storage may only move between them through rc_memcpy_peer / rc_device_wait (cf. DeviceFaer::same_device =
+ * equal pool size & order, device_faer/device.rs:46-51) */
+int rc_device_same_device(const rc_device *a, const rc_device *b, int *same);
+/* NUMA node of the GPU's PCIe root (from /sys/bus/pci/devices/<bus id>/numa_node), -1 if unknown */
+int rc_device_numa_node(const rc_device *dev, int *node);
 int rc_device_ordinal(const rc_device *dev, int *ordinal);
 int rc_device_stream(const rc_device *dev, void **cuda_stream);
 int rc_device_synchronize(rc_device *dev);
@@ -226,6 +231,11 @@ int rc_get_index(rc_device *dev, rc_dtype dtype, const void *a, int64_t index, v
 int rc_set_index(rc_device *dev, rc_dtype dtype, void *a, int64_t index, const void *host_value);
 /* pinned host staging buffers for outof_cpu_vec / to_cpu_vec */
 int rc_host_alloc(size_t nbytes, void **out);
+/* same, with the pages placed on NUMA node `node` before they are pinned: mbind(MPOL_BIND) (*bound_out = 1), or --
+ * where the container filters mbind -- first touch from a CPU of that node (*bound_out = 2); node < 0 = no placement;
+ * a failed placement is not an error: the buffer is still pinned, *bound_out = 0.  Staging buffers on the GPU's own
+ * socket keep H2D / D2H copies off the inter-socket link.  Free with rc_host_free. */
+int rc_host_alloc_on_node(size_t nbytes, int node, void **out, int *bound_out);
 int rc_host_free(void *ptr);
 size_t rc_dtype_size(rc_dtype dtype);
 
@@ -269,6 +279,10 @@ int rc_assign(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtyp
  * F for col-major); shapes may differ, sizes must match.  (Reference spelling "arbitary" kept.) */
 int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta, const void *a,
                        const rc_layout *la);
+/* same with the pairing order given explicitly instead of taken from the handle (reshape / to_layout with an order
+ * argument must not mutate a handle other threads share) */
+int rc_assign_arbitary_order(rc_device *dev, rc_order order, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta,
+                             const void *a, const rc_layout *la);
 /* c[idx] = cast(fill); *fill is a host scalar of dtype tf */
 int rc_fill(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype tf, const void *fill);
 
@@ -312,6 +326,37 @@ int rc_unary_muta(rc_device *dev, rc_unop op, rc_dtype dtype, void *a, const rc_
 int rc_redop_out_dtype(rc_redop op, rc_dtype dtype, rc_dtype *out);
 /* output dtype of an elementwise op for operand dtype `dtype` (bool for comparisons/predicates) */
 int rc_binop_out_dtype(rc_binop op, rc_dtype dtype, rc_dtype *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Mixed operand types: the 15 binary-function traits are generic over <TA, TB> and promote
+ * (rstsr-core/src/operators/ops/op_ternary_common.rs:22-57; impls
+ * rstsr-core/src/feature_rayon/auto_impl/op_ternary_common.rs:6-120):
+ *   R = DTypePromoteAPI<TB>::Res of TA   (NumPy's table, rstsr-dtype-traits/src/promotion.rs:186-300:
+ *                                          i32 x f32 -> f64, i8 x u8 -> i16, i64 x u64 -> f64, bool x T -> T ...)
+ *   atan2 copysign hypot nextafter logaddexp : both operands -> R -> DTypeIntoFloatAPI (ints -> f64), TOut = that float
+ *   maximum minimum floor_divide             : both -> R, TOut = R
+ *   == != < <= > >=                          : both -> R, TOut = bool
+ *   pow                                      : num::Pow<TB> for TA: float x same float (powf), float x i8/u8/i16/u16/i32
+ *                                              (powi), int x u8/u16/u32/u64 (wrapping power); TOut = TA
+ *   + - * / % | & ^ << >>                    : both -> R, TOut = R (the reference requires TA: Op<TB>; its tensor layer
+ *                                              promotes first)
+ * `tc` must be rc_binop_out_dtype_ex(op, ta, tb), else RC_ERR_INVALID_VALUE.  ta == tb runs the single fused kernel
+ * of rc_op_mutc_refa_refb; otherwise the operand(s) whose type differs from the compute type are cast first
+ * (element-exact `as` casts, broadcast axes kept compact), then the same kernel runs: results are bit-identical to
+ * promote_pair + into_float + f per element.
+ * ---------------------------------------------------------------------------------------- */
+int rc_dtype_promote(rc_dtype ta, rc_dtype tb, rc_dtype *out);
+int rc_binop_out_dtype_ex(rc_binop op, rc_dtype ta, rc_dtype tb, rc_dtype *out);
+int rc_op_mutc_refa_refb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta,
+                            const void *a, const rc_layout *la, rc_dtype tb, const void *b, const rc_layout *lb);
+int rc_op_mutc_refa_numb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta,
+                            const void *a, const rc_layout *la, rc_dtype tb, const void *b_host_scalar);
+int rc_op_mutc_numa_refb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta,
+                            const void *a_host_scalar, rc_dtype tb, const void *b, const rc_layout *lb);
+/* OpIsCloseAPI (rstsr-core/src/operators/ops/op_ternary_common.rs:59-102; isclose of
+ * rstsr-dtype-traits/src/isclose.rs:92-106 with TE = f64): c (bool) = |a-b| <= atol + rtol*|b| || (equal_nan && both NaN) */
+int rc_isclose(rc_device *dev, rc_dtype dtype, void *c_bool, const rc_layout *lc, const void *a, const rc_layout *la,
+               const void *b, const rc_layout *lb, double rtol, double atol, int equal_nan);
 int rc_unop_out_dtype(rc_unop op, rc_dtype dtype, rc_dtype *out);
 
 /* ------------------------------------------------------------------------------------------
@@ -385,12 +430,30 @@ typedef struct rc_comm rc_comm;
 int rc_comm_get_unique_id(uint8_t id[RC_COMM_ID_BYTES]);
 int rc_comm_init_rank(rc_device *dev, int nranks, int rank, const uint8_t id[RC_COMM_ID_BYTES], rc_comm **out);
 int rc_comm_destroy(rc_comm *comm);
+/* *nranks, *rank of the communicator; *peer_window = 1 when results up to 256 KiB are combined through the
+ * NVLink peer window (one kernel: fold of the local partial states + stores into every rank's window + rank-ordered
+ * fold; bitwise identical on all ranks and run to run) instead of ncclAllReduce.  RC_COMM_PEER=0 in the environment
+ * disables the window (NCCL only); RC_COMM_TIMEOUT_S bounds the in-kernel wait for a lost rank (default 120 s,
+ * then the kernel traps instead of hanging the job).  Any out pointer may be NULL. */
+int rc_comm_info(const rc_comm *comm, int *nranks, int *rank, int *peer_window);
 /* in-place all-reduce of `count` elements with the reduction's combiner (sum/prod/max/min; mean = sum,
- * the caller divides by the global count via rc_op_muta_numb) on the device's stream */
+ * the caller divides by the global count via rc_op_muta_numb) on the device's stream.  All element types
+ * (16-bit integers have no NCCL type: they go through the window, or widened to 32 bits above its size). */
 int rc_comm_all_reduce(rc_comm *comm, rc_redop op, rc_dtype dtype, void *buf_dev, size_t count);
-/* sharded `*_all`: local partial + all-reduce + host scalar; n_global is the global element count (mean) */
+/* sharded `*_all` (reduce_all_cpu_rayon, rstsr-native-impl/src/cpu_rayon/reduction.rs:20-106, with the closures of
+ * rstsr-core/src/feature_rayon/auto_impl/reduction.rs:14-63): local partial + cross-GPU combine + host scalar;
+ * n_global is the GLOBAL element count (mean = combined sum / n_global; max / min of n_global == 0 is
+ * RC_ERR_INVALID_VALUE on every rank).  A rank whose shard is empty contributes the monoid identity. */
 int rc_reduce_all_sharded(rc_device *dev, rc_comm *comm, rc_redop op, rc_dtype dtype, const void *a,
                           const rc_layout *la, int64_t n_global, void *host_out);
+/* sharded `*_axes` where the SHARDED axis is among the reduced ones (reduce_axes_cpu_rayon,
+ * rstsr-native-impl/src/cpu_rayon/reduction.rs:109-328): `la` is this rank's shard, (out_dev, lo) the full-size
+ * output (identical layout on every rank, shape = kept axes); every rank ends with the complete result.
+ * n_reduced_global = product of the reduced extents of the UNSHARDED tensor (the mean's divisor).
+ * sum / prod / max / min / mean. */
+int rc_reduce_axes_sharded(rc_device *dev, rc_comm *comm, rc_redop op, rc_dtype dtype, const void *a,
+                           const rc_layout *la, const int64_t *axes, int naxes, int64_t n_reduced_global, void *out_dev,
+                           const rc_layout *lo);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,17 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* The timed CPU baseline mirrors DeviceFaer::default() = the rayon global pool = every core the process may run on
+ * (rstsr-core/src/feature_rayon/device.rs:53-75).  Launchers such as torchrun export OMP_NUM_THREADS=1, which would
+ * silently turn the baseline into a single-thread run: the bench sets the count explicitly. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---- IterLayoutColMajor (iterator.rs:122-197): axis 0 fastest; position k -> offset ---- */
 typedef struct {
     const orc_layout *l;

@@ -130,6 +130,17 @@ SIGNATURES = {
     "rc_comm_destroy": (c_int, [_P]),
     "rc_comm_all_reduce": (c_int, [_P, c_int, c_int, _P, c_size_t]),
     "rc_reduce_all_sharded": (c_int, [_P, _P, c_int, c_int, _P, _L, c_int64, _P]),
+    "rc_comm_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "rc_reduce_axes_sharded": (c_int, [_P, _P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, c_int64, _P, _L]),
+    "rc_device_numa_node": (c_int, [_P, POINTER(c_int)]),
+    "rc_host_alloc_on_node": (c_int, [c_size_t, c_int, POINTER(_P), POINTER(c_int)]),
+    "rc_assign_arbitary_order": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, _L]),
+    "rc_dtype_promote": (c_int, [c_int, c_int, POINTER(c_int)]),
+    "rc_binop_out_dtype_ex": (c_int, [c_int, c_int, c_int, POINTER(c_int)]),
+    "rc_op_mutc_refa_refb_ex": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, _L, c_int, _P, _L]),
+    "rc_op_mutc_refa_numb_ex": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, _L, c_int, _P]),
+    "rc_op_mutc_numa_refb_ex": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, c_int, _P, _L]),
+    "rc_isclose": (c_int, [_P, c_int, _P, _L, _P, _L, _P, _L, c_double, c_double, c_int]),
 }
 
 _lib = None

@@ -13,6 +13,7 @@
 namespace rc {
 
 const std::string &last_error_ref();
+bool host_free_numa(void *ptr);  // rc_api_ex.cu
 
 void *workspace(rc_device *d, size_t nbytes) {
     if (nbytes <= d->ws_bytes) return d->ws;
@@ -170,8 +171,8 @@ std::vector<int> all_axes(int ndim) {
     return r;
 }
 
-void reduce_into(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const Layout &la, const std::vector<int> &axes,
-                 void *out, const Layout &lo) {
+void reduce_into_nolock(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const Layout &la,
+                        const std::vector<int> &axes, void *out, const Layout &lo) {
     if (op == RC_MAX || op == RC_MIN)
         RC_CHECK(la.size() != 0, RC_ERR_INVALID_VALUE,
                  op == RC_MAX ? "zero-size array is not supported for max" : "zero-size array is not supported for min");
@@ -184,11 +185,26 @@ void reduce_into(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const L
     Layout l_axes;
     split_axes(la, axes, &l_axes, nullptr, nullptr);  // validates both halves like the reference
     CanonRed cr = canon_reduce(la, axes, lo, /*keep_order=*/arg);
-    std::lock_guard<std::mutex> lock(dev->ws_mu);
     run_reduce(dev, op, t, cr, a, out, l_axes.size());
 }
 
+void reduce_into(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const Layout &la, const std::vector<int> &axes,
+                 void *out, const Layout &lo) {
+    std::lock_guard<std::mutex> lock(dev->ws_mu);
+    dev->preq = rc_device::PartialReq();
+    reduce_into_nolock(dev, op, t, a, la, axes, out, lo);
+}
+
 }  // namespace
+
+void cast_host_scalar(rc_dtype tc, rc_dtype tf, const void *src, void *out8) { host_scalar_cast(tc, tf, src, out8); }
+
+// for rc_comm.cu (sharded reductions): the caller holds dev->ws_mu and has set dev->preq
+void reduce_local(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const Layout &la, const std::vector<int> &axes,
+                  void *out, const Layout &lo) {
+    reduce_into_nolock(dev, op, t, a, la, axes, out, lo);
+}
+
 }  // namespace rc
 
 using namespace rc;
@@ -266,7 +282,7 @@ int rc_device_set_default_order(rc_device *dev, rc_order order) {
 int rc_device_same_device(const rc_device *a, const rc_device *b, int *same) {
     return guard([&] {
         RC_CHECK(a && b && same, RC_ERR_INVALID_VALUE, "null argument");
-        *same = (a->ordinal == b->ordinal && a->order == b->order) ? 1 : 0;
+        *same = (a->ordinal == b->ordinal && a->order == b->order && a->stream == b->stream) ? 1 : 0;
     });
 }
 int rc_device_ordinal(const rc_device *dev, int *ordinal) {
@@ -438,7 +454,11 @@ int rc_host_alloc(size_t nbytes, void **out) {
     });
 }
 int rc_host_free(void *ptr) {
-    return guard([&] { if (ptr) RC_CUDA(cudaFreeHost(ptr)); });
+    return guard([&] {
+        if (!ptr) return;
+        if (host_free_numa(ptr)) return;  // rc_host_alloc_on_node block (rc_api_ex.cu)
+        RC_CUDA(cudaFreeHost(ptr));
+    });
 }
 size_t rc_dtype_size(rc_dtype t) {
     size_t s = 0;
@@ -504,7 +524,7 @@ int rc_assign(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc_, rc_dty
     return guard([&] {
         DeviceGuard g(dev);
         Layout lc = from_c(lc_), la = from_c(la_);
-        CanonEw cn = canon_elementwise({&lc, &la}, false);
+        CanonEw cn = canon_elementwise({&lc, &la}, false, true);
         if (cn.empty) return;
         check_ptr(c, "c"); check_ptr(a, "a");
         EwArgs args;
@@ -514,23 +534,25 @@ int rc_assign(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc_, rc_dty
     });
 }
 
-int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc_, rc_dtype ta, const void *a,
-                       const rc_layout *la_) {
+static int assign_arbitary_impl(rc_device *dev, const rc_order *order_in, rc_dtype tc, void *c, const rc_layout *lc_,
+                               rc_dtype ta, const void *a, const rc_layout *la_) {
     return guard([&] {
         DeviceGuard g(dev);
+        const rc_order order = order_in ? *order_in : dev->order;
+        RC_CHECK(order == RC_ROW_MAJOR || order == RC_COL_MAJOR, RC_ERR_INVALID_VALUE, "invalid order");
         Layout lc = from_c(lc_), la = from_c(la_);
         RC_CHECK(lc.size() == la.size(), RC_ERR_INVALID_LAYOUT, "assign_arbitary requires layouts of equal size");
         if (lc.size() == 0) return;
         check_ptr(c, "c"); check_ptr(a, "a");
         Layout rc_, ra_;
-        if (refine_to_common_shape(lc, la, dev->order, &rc_, &ra_)) {
+        if (refine_to_common_shape(lc, la, order, &rc_, &ra_)) {
             CanonEw cn = canon_elementwise({&rc_, &ra_}, false);
             EwArgs args;
             args.c = c;
             args.a = a;
             run_cast(dev, tc, ta, cn, args);
         } else if (tc == ta) {
-            run_assign_arbitrary_generic(dev, tc, c, lc, ta, a, la, dev->order);
+            run_assign_arbitrary_generic(dev, tc, c, lc, ta, a, la, order);
         } else {
             // rare: strided views of incompatible shapes AND a cast -- stage the cast through a flat buffer
             // (a 1-D contiguous layout has a common refinement with every shape)
@@ -540,13 +562,13 @@ int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc
             if (e != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
             try {
                 Layout f1, a1;
-                RC_CHECK(refine_to_common_shape(flat, la, dev->order, &f1, &a1), RC_ERR_RUNTIME, "refinement of a flat layout");
+                RC_CHECK(refine_to_common_shape(flat, la, order, &f1, &a1), RC_ERR_RUNTIME, "refinement of a flat layout");
                 CanonEw cn = canon_elementwise({&f1, &a1}, false);
                 EwArgs args;
                 args.c = tmp;
                 args.a = a;
                 run_cast(dev, tc, ta, cn, args);
-                run_assign_arbitrary_generic(dev, tc, c, lc, tc, tmp, flat, dev->order);
+                run_assign_arbitrary_generic(dev, tc, c, lc, tc, tmp, flat, order);
             } catch (...) {
                 cudaFreeAsync(tmp, dev->stream);
                 throw;
@@ -554,6 +576,15 @@ int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc
             RC_CUDA(cudaFreeAsync(tmp, dev->stream));
         }
     });
+}
+
+int rc_assign_arbitary(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta, const void *a,
+                       const rc_layout *la) {
+    return assign_arbitary_impl(dev, nullptr, tc, c, lc, ta, a, la);
+}
+int rc_assign_arbitary_order(rc_device *dev, rc_order order, rc_dtype tc, void *c, const rc_layout *lc, rc_dtype ta,
+                             const void *a, const rc_layout *la) {
+    return assign_arbitary_impl(dev, &order, tc, c, lc, ta, a, la);
 }
 
 int rc_fill(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc_, rc_dtype tf, const void *fill) {
@@ -576,7 +607,7 @@ int rc_op_mutc_refa_refb(rc_device *dev, rc_binop op, rc_dtype t, void *c, const
     return guard([&] {
         DeviceGuard g(dev);
         Layout lc = from_c(lc_), la = from_c(la_), lb = from_c(lb_);
-        CanonEw cn = canon_elementwise({&lc, &la, &lb}, false);
+        CanonEw cn = canon_elementwise({&lc, &la, &lb}, false, true);
         if (cn.empty) return;
         check_ptr(c, "c"); check_ptr(a, "a"); check_ptr(b, "b");
         EwArgs args;
@@ -590,7 +621,7 @@ int rc_op_mutc_refa_numb(rc_device *dev, rc_binop op, rc_dtype t, void *c, const
     return guard([&] {
         DeviceGuard g(dev);
         Layout lc = from_c(lc_), la = from_c(la_);
-        CanonEw cn = canon_elementwise({&lc, &la}, false);
+        CanonEw cn = canon_elementwise({&lc, &la}, false, true);
         if (cn.empty) return;
         check_ptr(c, "c"); check_ptr(a, "a"); check_ptr(b_host, "b");
         EwArgs args;
@@ -604,7 +635,7 @@ int rc_op_mutc_numa_refb(rc_device *dev, rc_binop op, rc_dtype t, void *c, const
     return guard([&] {
         DeviceGuard g(dev);
         Layout lc = from_c(lc_), lb = from_c(lb_);
-        CanonEw cn = canon_elementwise({&lc, &lb}, false);
+        CanonEw cn = canon_elementwise({&lc, &lb}, false, true);
         if (cn.empty) return;
         check_ptr(c, "c"); check_ptr(b, "b"); check_ptr(a_host, "a");
         EwArgs args;
@@ -657,7 +688,7 @@ int rc_unary_muta_refb(rc_device *dev, rc_unop op, rc_dtype t, void *a, const rc
     return guard([&] {
         DeviceGuard g(dev);
         Layout la = from_c(la_), lb = from_c(lb_);
-        CanonEw cn = canon_elementwise({&la, &lb}, false);
+        CanonEw cn = canon_elementwise({&la, &lb}, false, true);
         if (cn.empty) return;
         check_ptr(a, "a"); check_ptr(b, "b");
         EwArgs args;

@@ -15,7 +15,7 @@ struct Dim {
 };
 }  // namespace
 
-CanonEw canon_elementwise(const std::vector<const Layout *> &ls, bool collapse_out_broadcast) {
+CanonEw canon_elementwise(const std::vector<const Layout *> &ls, bool collapse_out_broadcast, bool drop_common_broadcast) {
     CanonEw c;
     c.nops = (int)ls.size();
     RC_CHECK(c.nops >= 1 && c.nops <= KMAXOPS, RC_ERR_RUNTIME, "operand count");
@@ -39,6 +39,11 @@ CanonEw canon_elementwise(const std::vector<const Layout *> &ls, bool collapse_o
         for (int k = 0; k < c.nops; ++k) d.s[k] = ls[k]->stride[i];
         if (d.s[0] == 0) {
             if (collapse_out_broadcast) continue;  // order G: a broadcast output axis is visited once
+            // both inputs broadcast along the axis too (x.broadcast_to(s) + y.broadcast_to(s): get_layout_for_binary_op
+            // gives the output stride 0 there): every visit would write the same value, so the axis is visited once
+            bool all_zero = drop_common_broadcast;
+            for (int k = 1; k < c.nops && all_zero; ++k) all_zero = d.s[k] == 0;
+            if (all_zero) continue;
             raise(RC_ERR_INVALID_LAYOUT, "output layout is broadcast (stride 0 on an axis of extent > 1)");
         }
         if (d.s[0] < 0) {  // walk the axis the other way round in every operand
@@ -202,6 +207,7 @@ CanonRed canon_reduce_binary(const Layout &lam, const Layout &lbm, const Layout 
         if (lo.shape[j] == 0) { c.empty_out = true; return c; }
         if (lo.shape[j] == 1) continue;
         K k{lo.shape[j], lam.stride[j], lbm.stride[j], lo.stride[j]};
+        if (k.so == 0 && k.sa == 0 && k.sb == 0) continue;  // kept axis broadcast in both inputs and the output: once
         RC_CHECK(k.so != 0, RC_ERR_INVALID_LAYOUT, "output layout is broadcast (stride 0 on an axis of extent > 1)");
         if (k.so < 0) {
             c.base_in += (k.n - 1) * k.sa; k.sa = -k.sa;

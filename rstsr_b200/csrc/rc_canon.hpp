@@ -27,7 +27,10 @@ struct CanonEw {
 
 // layouts[0] is the output.  `collapse_out_broadcast`: iteration order G (in-place unary / fill): axes
 // where the output has stride 0 are visited once.  A broadcast output is otherwise rejected.
-CanonEw canon_elementwise(const std::vector<const Layout *> &layouts, bool collapse_out_broadcast);
+// `drop_common_broadcast`: an axis where the output AND every input have stride 0 is visited once instead of being
+// rejected -- only valid when the output storage is not also an input (out-of-place ops).
+CanonEw canon_elementwise(const std::vector<const Layout *> &layouts, bool collapse_out_broadcast,
+                          bool drop_common_broadcast = false);
 
 // Rewrites (lc, la) of equal SIZE but different shape into two layouts of one common refined shape such
 // that same-index pairing equals flattened-order pairing in `order` (assign_arbitary semantics,

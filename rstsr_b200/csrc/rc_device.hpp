@@ -17,6 +17,15 @@ struct rc_device {
     std::mutex ws_mu;
     void *ws = nullptr;
     size_t ws_bytes = 0;
+    // Sharded reductions (rc_comm.cu) ask the two-pass launchers to stop after the FIRST pass: the fold over the
+    // local partial states is fused into the cross-GPU combine kernel.  Set / read under ws_mu.
+    struct PartialReq {
+        bool want = false;      // in: stop after the first pass when the policy's state is its element type
+        bool got = false;       // out: `ptr` holds states[S][pitch]; `out` was not written
+        const void *ptr = nullptr;
+        int64_t S = 0, pitch = 0;
+        void *out = nullptr;    // typed output pointer (base offset applied), contiguous in canonical order
+    } preq;
     // 64-byte pinned + mapped host slot: kernels of `*_all` reductions write their scalar straight into host
     // memory, so the call costs launch + stream sync (no allocation, no D2H copy).  Held under slot_mu from the
     // launch until the host has read the value.

@@ -34,6 +34,18 @@ struct EwConst {  // scalar operand slot; T may be any POD
     T v;
 };
 
+// Run-time parameters of a functor (isclose: rtol / atol / equal_nan): a functor that declares `using Params = ...`
+// receives them as the last argument of apply(); every other functor gets an empty struct the compiler drops.
+struct EwNoParams {};
+template <class F, class = void> struct ew_params { using type = EwNoParams; };
+template <class F> struct ew_params<F, std::void_t<typename F::Params>> { using type = typename F::Params; };
+template <class F> using ew_params_t = typename ew_params<F>::type;
+template <class F>
+__device__ __forceinline__ typename F::TO ew_apply(typename F::TA x, typename F::TB y, const ew_params_t<F> &prm) {
+    if constexpr (std::is_same<ew_params_t<F>, EwNoParams>::value) return F::apply(x, y);
+    else return F::apply(x, y, prm);
+}
+
 // offsets of work item `idx` in the three operands.  ND = 1, 2: compile-time rank (no loop, at most one
 // division); ND = 0: runtime rank d.ndim <= KMAXD.
 template <int ND>
@@ -65,7 +77,8 @@ __device__ __forceinline__ void ew_item_offsets(const EwDesc<3> &d, uint32_t idx
 template <class F, int VEC, int ND>
 __global__ void __launch_bounds__(EW_BLOCK) ew_kernel(const __grid_constant__ EwDesc<3> d, typename F::TO *c, const typename F::TA *a,
                                                       const typename F::TB *b, int mode_a, int mode_b,
-                                                      EwConst<typename F::TA> ka, EwConst<typename F::TB> kb) {
+                                                      EwConst<typename F::TA> ka, EwConst<typename F::TB> kb,
+        ew_params_t<F> prm) {
     using TA = typename F::TA;
     using TB = typename F::TB;
     using TO = typename F::TO;
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_kernel(const __grid_constant__ Ew
                 const TA x = (VEC > 1 && spl_a) ? sa[u].v[0] : va[u].v[j];
                 if constexpr (F::NIN > 1) {
                     const TB y = (VEC > 1 && spl_b) ? sb[u].v[0] : vb[u].v[j];
-                    r.v[j] = F::apply(x, y);
+                    r.v[j] = ew_apply<F>(x, y, prm);
                 } else {
                     r.v[j] = F::apply(x);
                 }
@@ -140,7 +153,7 @@ template <class F, int VEC>
 __global__ void __launch_bounds__(EW_BLOCK) ew_rows_kernel(const __grid_constant__ EwRowsDesc d, typename F::TO *c,
                                                            const typename F::TA *a, const typename F::TB *b,
                                                            int mode_a, int mode_b, EwConst<typename F::TA> ka,
-                                                           EwConst<typename F::TB> kb) {
+                                                           EwConst<typename F::TB> kb, ew_params_t<F> prm) {
     using TA = typename F::TA;
     using TB = typename F::TB;
     using TO = typename F::TO;
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_rows_kernel(const __grid_constant
                 Pack<TO, VEC> r;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    if constexpr (F::NIN > 1) r.v[j] = F::apply(va[u].v[j], vb[u].v[j]);
+                    if constexpr (F::NIN > 1) r.v[j] = ew_apply<F>(va[u].v[j], vb[u].v[j], prm);
                     else r.v[j] = F::apply(va[u].v[j]);
                 }
                 st_stream<TO, VEC>(pc + u * step_c, r);
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
                                                                    const typename F::TA *a, const typename F::TB *b,
                                                                    int mode_a, int mode_b,
                                                                    EwConst<typename F::TA> ka,
-                                                                   EwConst<typename F::TB> kb) {
+                                                                   EwConst<typename F::TB> kb, ew_params_t<F> prm) {
     using TA = typename F::TA;
     using TB = typename F::TB;
     using TO = typename F::TO;
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
                 TO out;
                 if constexpr (F::NIN > 1) {
                     const TB vb = stg_b ? sb[v * PITCH + u] : rb[r][j].v[0];
-                    out = F::apply(va, vb);
+                    out = ew_apply<F>(va, vb, prm);
                 } else {
                     out = F::apply(va);
                 }
@@ -506,7 +519,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_rect_kernel(const __g
                                                                         typename F::TO *c, const typename F::TA *a,
                                                                         const typename F::TB *b, int mode_a, int mode_b,
                                                                         EwConst<typename F::TA> ka,
-                                                                        EwConst<typename F::TB> kb) {
+                                                                        EwConst<typename F::TB> kb, ew_params_t<F> prm) {
     using TA = typename F::TA;
     using TB = typename F::TB;
     using TO = typename F::TO;
@@ -569,7 +582,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_rect_kernel(const __g
         TO out;
         if constexpr (F::NIN > 1) {
             const TB vb = stg_b ? rect_lds<TB>(sb + si * (uint32_t)sizeof(TB)) : rb[s].v[0];
-            out = F::apply(va, vb);
+            out = ew_apply<F>(va, vb, prm);
         } else {
             out = F::apply(va);
         }
@@ -585,6 +598,7 @@ struct EwArgs {
     const void *a = nullptr, *b = nullptr;
     bool a_const = false, b_const = false;  // operand is a host scalar
     const void *a_host = nullptr, *b_host = nullptr;
+    const void *params = nullptr;           // host copy of F::Params for functors that declare one
 };
 
 // Splits a canonical problem until it fits one launch (<= KMAXD dims, < 2^31 items); fn(part).
@@ -645,6 +659,11 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
         else { slot_b = slot++; pb = static_cast<const TB *>(args.b) + c.base[slot_b]; mode_b = MODE_MEM; }
     }
     if (NIN == 0 && args.a_host) std::memcpy(&ka.v, args.a_host, sizeof(TA));  // fill value
+    ew_params_t<F> prm;
+    if constexpr (!std::is_same<ew_params_t<F>, EwNoParams>::value) {
+        RC_CHECK(args.params != nullptr, RC_ERR_INVALID_VALUE, "internal: functor parameters missing");
+        std::memcpy(&prm, args.params, sizeof(prm));
+    }
 
     auto stride_of = [&](int s, int i) -> int64_t { return s < 0 ? 0 : c.stride[s][i]; };
 
@@ -758,7 +777,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                             RC_CUDA(cudaFuncSetAttribute(ew_tile_rect_kernel<F>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         ew_tile_rect_kernel<F><<<r.total_tiles, TILE_WARPS * 32, smem, dev->stream>>>(r, pc, pa, pb, tm_a,
-                                                                                                    tm_b, ka, kb);
+                                                                                                    tm_b, ka, kb, prm);
                         after_launch(dev, "ew_tile_rect_kernel");
                         return;
                     }
@@ -770,7 +789,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                     if (smem > 48 * 1024)  // opt in to > 48 KB dynamic shared memory (per device)
                         RC_CUDA(cudaFuncSetAttribute(ew_tile_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int)smem));
-                    ew_tile_kernel<F><<<t.total_tiles, TILE_WARPS * 32, smem, dev->stream>>>(t, pc, pa, pb, tm_a, tm_b, ka, kb);
+                    ew_tile_kernel<F><<<t.total_tiles, TILE_WARPS * 32, smem, dev->stream>>>(t, pc, pa, pb, tm_a, tm_b, ka, kb, prm);
                     after_launch(dev, "ew_tile_kernel");
                     return;
                 }
@@ -800,7 +819,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
             if (slot_a >= 0 && c.stride[slot_a][0] == 0) mode_a = MODE_SPLAT;
             if (slot_b >= 0 && c.stride[slot_b][0] == 0) mode_b = MODE_SPLAT;
             if (c.ndim == 1) {
-                ew_kernel<F, V, 1><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+                ew_kernel<F, V, 1><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
             } else if (c.ndim == 2 && c.shape[0] / V >= 512 && c.shape[1] < (1ll << 31) &&
                        // a splat operand that changes from row to row stays on the flat kernel: the rows kernel would be
                        // correct with one row per CTA, but its dependent scalar load at the head of every CTA measured slower
@@ -827,24 +846,24 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                 int64_t groups = (rd.n1 + rd.rows_per_cta - 1) / rd.rows_per_cta;
                 int64_t g2 = groups * chunks;
                 if (g2 < (1ll << 31)) {
-                    ew_rows_kernel<F, V><<<(unsigned)g2, EW_BLOCK, 0, dev->stream>>>(rd, pc, pa, pb, mode_a, mode_b, ka, kb);
+                    ew_rows_kernel<F, V><<<(unsigned)g2, EW_BLOCK, 0, dev->stream>>>(rd, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
                     after_launch(dev, "ew_rows_kernel");
                     return;
                 }
-                ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+                ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
             } else {
                 // (a compile-time rank-2 instance of the VECTOR kernel was measured too: outer sum unchanged at 4.4 TB/s,
                 // (n,n) + (n,1) 6.76 -> 6.51 TB/s -- profiles/r01_results/probe_ew_nd2_all.txt -- so packs keep the
                 // runtime-rank walk; the scalar path below is where rank 2 pays)
-                ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+                ew_kernel<F, V, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
             }
             after_launch(dev, "ew_kernel");
             return;
         }
     }
     // scalar path: element-rate bound, so 2-D problems take the compile-time rank (f32 a[:, 1:-1] copy 3.8 -> 5.45 TB/s)
-    if (c.ndim == 2) ew_kernel<F, 1, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
-    else ew_kernel<F, 1, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb);
+    if (c.ndim == 2) ew_kernel<F, 1, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
+    else ew_kernel<F, 1, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
     after_launch(dev, "ew_kernel");
 }
 

@@ -17,4 +17,23 @@ void run_binary_func(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, 
     unsupported("binary function", t);
 }
 
+// pow with a mixed exponent: t = base type; the exponent operand is i32 (float base) or u32 (integer base)
+void run_binary_pow_mixed(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args) {
+    switch (t) {
+        RC_SWITCH_FLOAT(FPowi)
+        RC_SWITCH_INT(FIPow)
+        default: break;
+    }
+    unsupported("pow", t);
+}
+
+// elementwise isclose, bool output; args.params -> IsCloseParams
+void run_isclose(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args) {
+    switch (t) {
+        RC_SWITCH_NUM(FIsClose)
+        default: break;
+    }
+    unsupported("isclose", t);
+}
+
 }  // namespace rc

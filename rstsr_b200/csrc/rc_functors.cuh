@@ -88,6 +88,57 @@ RC_FLOAT_BINARY(FHypot, hypotf(a, b), hypot(a, b))
 RC_FLOAT_BINARY(FLogAddExp, logf(expf(a) + expf(b)), log(exp(a) + exp(b)))
 RC_FLOAT_BINARY(FNextAfter, nextafterf(a, b), nextafter(a, b))
 
+// pow with a mixed exponent (num::Pow<TB> for TA, the bound of OpPowAPI: auto_impl/op_ternary_common.rs:141-149):
+//   float ^ i8/u8/i16/u16/i32 = powi: compiler-rt's __powi?f2 (square-and-multiply from the low bit, reciprocal at the
+//   end for negative exponents) -- restated so the result is bit-identical to Rust's f32::powi / f64::powi;
+//   int ^ u8/u16/u32/u64 = wrapping power (release-mode {integer}::pow); the exponent arrives as u32.
+template <class T> struct FPowi { using TA = T; using TB = int32_t; using TO = T; static constexpr int NIN = 2;
+    RC_FN T apply(T a, int32_t b) {
+        const bool recip = b < 0;
+        T r = (T)1;
+        while (true) {
+            if (b & 1) r *= a;
+            b /= 2;
+            if (b == 0) break;
+            a *= a;
+        }
+        return recip ? (T)1 / r : r; } };
+template <class T> struct FIPow { using TA = T; using TB = uint32_t; using TO = T; static constexpr int NIN = 2;
+    RC_FN T apply(T a, uint32_t e) {
+        using U = typename std::conditional<(sizeof(T) < 4), uint32_t, uns_t<T>>::type;
+        U base = (U)(uns_t<T>)a, r = 1;
+        while (e) {
+            if (e & 1u) r *= base;
+            base *= base;
+            e >>= 1;
+        }
+        return (T)(uns_t<T>)r; } };
+
+// isclose (rstsr-dtype-traits/src/isclose.rs:92-106) with TE = f64: diff and |b| are formed in the element type,
+// then cast; inf vs inf gives |inf - inf| = NaN -> not close, as in the reference.
+struct IsCloseParams { double rtol, atol; int equal_nan; };
+template <class T> struct FIsClose { using TA = T; using TB = T; using TO = uint8_t; static constexpr int NIN = 2;
+    using Params = IsCloseParams;
+    RC_FN uint8_t apply(T a, T b, const IsCloseParams &p) {
+        double diff, abs_b;
+        if constexpr (std::is_floating_point<T>::value) {
+            const T df = a - b;
+            diff = (double)(df < (T)0 ? -df : df);
+            abs_b = (double)(b < (T)0 ? -b : b);
+            if (df != df) diff = (double)df;
+            if (b != b) abs_b = (double)b;
+        } else if constexpr (std::is_signed<T>::value) {
+            const T df = a >= b ? (T)((uns_t<T>)a - (uns_t<T>)b) : (T)((uns_t<T>)b - (uns_t<T>)a);
+            diff = (double)df;
+            abs_b = (double)(b < 0 ? (T)((uns_t<T>)0 - (uns_t<T>)b) : b);
+        } else {
+            diff = (double)(a >= b ? (T)(a - b) : (T)(b - a));
+            abs_b = (double)b;
+        }
+        bool ok = diff <= p.atol + p.rtol * abs_b;
+        if constexpr (std::is_floating_point<T>::value) ok = ok || (p.equal_nan && a != a && b != b);
+        return ok ? 1 : 0; } };
+
 // ---------------- comparisons: TO = bool ----------------
 #define RC_COMPARE(NAME, EXPR)                                                                  \
     template <class T> struct NAME { using TA = T; using TB = T; using TO = uint8_t; static constexpr int NIN = 2; \

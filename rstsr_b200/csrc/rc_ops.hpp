@@ -12,6 +12,11 @@ void run_binary_arith(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c,
 void run_binary_bit(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
 void run_binary_func(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
 void run_binary_cmp(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+// pow with a mixed exponent (i32 for a float base, u32 for an integer base) and elementwise isclose (rc_ew_func.cu)
+void run_binary_pow_mixed(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args);
+void run_isclose(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args);
+// Rust `as` between host scalars (rc_api.cu): 8 bytes out
+void cast_host_scalar(rc_dtype tc, rc_dtype tf, const void *src, void *out8);
 // a = f(b)
 void run_unary(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
 // c = cast(a) (rc_copy.cu); same dtype moves raw bits
@@ -25,5 +30,11 @@ void run_assign_arbitrary_generic(rc_device *dev, rc_dtype tc, void *c, const La
 // reductions (rc_reduce.cu): out has n_out elements laid out by `cr`
 void run_reduce(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out,
                 int64_t mean_count);
+
+// reduction of `a` over `axes` into (out, lo) WITHOUT taking dev->ws_mu (rc_api.cu): the caller holds the lock and
+// owns dev->preq (see rc_device.hpp) -- used by the sharded reductions of rc_comm.cu
+void reduce_local(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const Layout &la, const std::vector<int> &axes,
+                  void *out, const Layout &lo);
+rc_dtype redop_out_dtype(rc_redop op, rc_dtype t);
 
 }  // namespace rc

@@ -723,6 +723,17 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     const bool kept_contig = d.nk >= 1 && d.ks_in[0] == 1 && (!BIN || d.ks_in2[0] == 1) && d.ks_out[0] == 1 &&
                              d.kshape[0] >= cols_min_extent();
 
+    // a sharded reduction folds the partial states itself (fused with the cross-GPU combine): possible when the state
+    // is the element (sum / prod / max / min) and output index o lives at out[o] (canonical order is contiguous)
+    auto fuse_second_pass = [&]() {
+        if (!dev->preq.want || !SIMPLE || BIN || !std::is_same<S, TO>::value) return false;
+        int64_t acc = 1;
+        for (size_t i = 0; i < c.kshape.size(); ++i) {
+            if (c.kstride_out[i] != acc) return false;
+            acc *= c.kshape[i];
+        }
+        return true;
+    };
     auto second_pass_desc = [&](const RedDesc &first, int64_t Sx) {
         RedDesc e = first;
         e.to_partial = 0;
@@ -772,6 +783,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         S *partial = static_cast<S *>(workspace(dev, (size_t)Sx * n_out * sizeof(S)));
         d.to_partial = 1;
         launch_cols<P, V>(dev, d, vec, Sx, in, in2, out, partial);
+        if (fuse_second_pass()) { dev->preq.got = true; dev->preq.ptr = partial; dev->preq.S = Sx; dev->preq.pitch = n_out; dev->preq.out = out; return; }
         // second pass: fold partial[S][n_out] over S, same kept dims with contiguous input strides
         RedDesc e = second_pass_desc(d, Sx);
         constexpr int V2 = SIMPLE ? V : 1;
@@ -852,6 +864,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     S *partial = static_cast<S *>(workspace(dev, (size_t)Sx * n_out * sizeof(S)));
     d.to_partial = 1;
     launch_rows<P, V>(dev, d, vec, Sx, in, in2, out, partial);
+    if (fuse_second_pass()) { dev->preq.got = true; dev->preq.ptr = partial; dev->preq.S = Sx; dev->preq.pitch = n_out; dev->preq.out = out; return; }
     // second pass: out[o] = fold_s partial[s][o]
     RedDesc e = second_pass_desc(d, Sx);
     e.group = (int)std::min<int64_t>(RED_BLOCK, std::max<int64_t>(1, pow2_floor(std::max<int64_t>(1, Sx / 2))));

@@ -329,6 +329,23 @@ class DeviceCuda:
         check(_ffi.lib().rc_memcpy2d_d2h_async(self._handle, host_ptr, host_pitch, raw.ptr + src_byte_offset, src_pitch,
                                                width_bytes, height))
 
+    def numa_node(self) -> int:
+        """NUMA node of the GPU's PCIe root (-1 if the platform does not say)."""
+        out = ctypes.c_int(-1)
+        check(_ffi.lib().rc_device_numa_node(self._handle, byref(out)))
+        return out.value
+
+    @staticmethod
+    def host_alloc(nbytes: int, node: int = -1) -> Tuple[int, bool]:
+        """Pinned staging buffer, optionally bound to a NUMA node: (address, bound?).  Free with host_free."""
+        p, bound = ctypes.c_void_p(), ctypes.c_int(0)
+        check(_ffi.lib().rc_host_alloc_on_node(int(nbytes), int(node), byref(p), byref(bound)))
+        return p.value, bool(bound.value)
+
+    @staticmethod
+    def host_free(ptr: int):
+        check(_ffi.lib().rc_host_free(ctypes.c_void_p(ptr)))
+
     def wrap(self, ptr: int, length: int, dtype) -> CudaRaw:
         """Borrow device memory owned by someone else (e.g. a torch tensor's data_ptr())."""
         return CudaRaw(self, ptr, length, dtype, owned=False)
@@ -349,9 +366,15 @@ class DeviceCuda:
 
     assign_uninit = assign
 
-    def assign_arbitary(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout):
-        check(_ffi.lib().rc_assign_arbitary(self._handle, dtype_code(c.dtype), c.ptr, byref(lc.to_c()),
-                                            dtype_code(a.dtype), a.ptr, byref(la.to_c())))
+    def assign_arbitary(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, order: Optional[int] = None):
+        """`order`: pairing order of the flattened elements; None = the handle's default order.  Passing it explicitly
+        (rc_assign_arbitary_order) keeps a handle that several threads share untouched."""
+        if order is None:
+            check(_ffi.lib().rc_assign_arbitary(self._handle, dtype_code(c.dtype), c.ptr, byref(lc.to_c()),
+                                                dtype_code(a.dtype), a.ptr, byref(la.to_c())))
+        else:
+            check(_ffi.lib().rc_assign_arbitary_order(self._handle, int(order), dtype_code(c.dtype), c.ptr,
+                                                      byref(lc.to_c()), dtype_code(a.dtype), a.ptr, byref(la.to_c())))
 
     assign_arbitary_uninit = assign_arbitary
 
@@ -368,21 +391,42 @@ class DeviceCuda:
         return np.array([value]).astype(dtype)
 
     def op_mutc_refa_refb(self, op: str, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout):
-        check(_ffi.lib().rc_op_mutc_refa_refb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), c.ptr, byref(lc.to_c()),
-                                              a.ptr, byref(la.to_c()), b.ptr, byref(lb.to_c())))
+        """c = a op b.  Operands of one dtype run the single fused kernel; mixed dtypes follow the reference's promotion
+        rules (rc_op_mutc_refa_refb_ex: DTypePromoteAPI / DTypeIntoFloatAPI).  c's dtype must be the op's output type
+        (the reference fixes it through `TOut`): anything else is a DTypeMismatch instead of reinterpreted bytes."""
+        want = self.binop_out_dtype_ex(op, a.dtype, b.dtype)
+        if c.dtype != want:
+            raise RstsrCudaError(6, f"DTypeMismatch: {op}({a.dtype}, {b.dtype}) writes {want}, output storage is {c.dtype}")
+        # rc_op_mutc_refa_refb_ex runs the single fused kernel of rc_op_mutc_refa_refb when no operand needs a cast
+        check(_ffi.lib().rc_op_mutc_refa_refb_ex(self._handle, _ffi.BINOPS[op], dtype_code(c.dtype), c.ptr,
+                                                 byref(lc.to_c()), dtype_code(a.dtype), a.ptr, byref(la.to_c()),
+                                                 dtype_code(b.dtype), b.ptr, byref(lb.to_c())))
 
-    def op_mutc_refa_numb(self, op: str, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b):
-        s = self._scalar(b, a.dtype)
-        check(_ffi.lib().rc_op_mutc_refa_numb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), c.ptr, byref(lc.to_c()),
-                                              a.ptr, byref(la.to_c()), s.ctypes.data))
+    def op_mutc_refa_numb(self, op: str, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b, b_dtype=None):
+        """b is a host scalar of a's dtype, or of `b_dtype` (then the pair is promoted like two tensors)."""
+        bt = a.dtype if b_dtype is None else np.dtype(b_dtype)
+        want = self.binop_out_dtype_ex(op, a.dtype, bt)
+        if c.dtype != want:
+            raise RstsrCudaError(6, f"DTypeMismatch: {op}({a.dtype}, {bt}) writes {want}, output storage is {c.dtype}")
+        s = self._scalar(b, bt)
+        check(_ffi.lib().rc_op_mutc_refa_numb_ex(self._handle, _ffi.BINOPS[op], dtype_code(c.dtype), c.ptr,
+                                                 byref(lc.to_c()), dtype_code(a.dtype), a.ptr, byref(la.to_c()),
+                                                 dtype_code(bt), s.ctypes.data))
 
-    def op_mutc_numa_refb(self, op: str, c: CudaRaw, lc: Layout, a, b: CudaRaw, lb: Layout):
-        s = self._scalar(a, b.dtype)
-        check(_ffi.lib().rc_op_mutc_numa_refb(self._handle, _ffi.BINOPS[op], dtype_code(b.dtype), c.ptr, byref(lc.to_c()),
-                                              s.ctypes.data, b.ptr, byref(lb.to_c())))
+    def op_mutc_numa_refb(self, op: str, c: CudaRaw, lc: Layout, a, b: CudaRaw, lb: Layout, a_dtype=None):
+        at = b.dtype if a_dtype is None else np.dtype(a_dtype)
+        want = self.binop_out_dtype_ex(op, at, b.dtype)
+        if c.dtype != want:
+            raise RstsrCudaError(6, f"DTypeMismatch: {op}({at}, {b.dtype}) writes {want}, output storage is {c.dtype}")
+        s = self._scalar(a, at)
+        check(_ffi.lib().rc_op_mutc_numa_refb_ex(self._handle, _ffi.BINOPS[op], dtype_code(c.dtype), c.ptr,
+                                                 byref(lc.to_c()), dtype_code(at), s.ctypes.data, dtype_code(b.dtype),
+                                                 b.ptr, byref(lb.to_c())))
 
     def op_muta_refb(self, op: str, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, reverse: bool = False):
         """a = a o b (Op*AssignAPI / OpLConsume*API); reverse: a = b o a (OpRConsume*API)."""
+        if a.dtype != b.dtype:  # `TA: AddAssign<TB>` etc.: the reference has no mixed-type in-place op
+            raise RstsrCudaError(6, f"DTypeMismatch: in-place {op} needs operands of one dtype ({a.dtype} vs {b.dtype})")
         check(_ffi.lib().rc_op_muta_refb(self._handle, _ffi.BINOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
                                          b.ptr, byref(lb.to_c()), 1 if reverse else 0))
 
@@ -403,6 +447,30 @@ class DeviceCuda:
         out = ctypes.c_int()
         check(_ffi.lib().rc_binop_out_dtype(_ffi.BINOPS[op], dtype_code(dtype), byref(out)))
         return dtype_np(out.value)
+
+    @staticmethod
+    def binop_out_dtype_ex(op: str, ta, tb) -> np.dtype:
+        """TOut of the op for operand types (ta, tb): rc_binop_out_dtype_ex (promotion rules of the reference)."""
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_binop_out_dtype_ex(_ffi.BINOPS[op], dtype_code(ta), dtype_code(tb), byref(out)))
+        return dtype_np(out.value)
+
+    @staticmethod
+    def promote_types(ta, tb) -> np.dtype:
+        """<TA as DTypePromoteAPI<TB>>::Res (rstsr-dtype-traits/src/promotion.rs)."""
+        out = ctypes.c_int()
+        check(_ffi.lib().rc_dtype_promote(dtype_code(ta), dtype_code(tb), byref(out)))
+        return dtype_np(out.value)
+
+    def isclose(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, rtol: float = 1.0e-5,
+                atol: float = 1.0e-8, equal_nan: bool = False):
+        """OpIsCloseAPI::op_mutc_refa_refb (rstsr-core/src/operators/ops/op_ternary_common.rs:67-82), TE = f64."""
+        if a.dtype != b.dtype:
+            raise RstsrCudaError(6, "DTypeMismatch: isclose takes operands of one dtype")
+        if c.dtype != np.dtype(np.bool_):
+            raise RstsrCudaError(6, "DTypeMismatch: isclose writes bool")
+        check(_ffi.lib().rc_isclose(self._handle, dtype_code(a.dtype), c.ptr, byref(lc.to_c()), a.ptr, byref(la.to_c()),
+                                    b.ptr, byref(lb.to_c()), float(rtol), float(atol), int(bool(equal_nan))))
 
     @staticmethod
     def unop_out_dtype(op: str, dtype) -> np.dtype:
@@ -437,6 +505,9 @@ class DeviceCuda:
         return CudaRaw(self, p.value, max(layout.size, 1), self.redop_out_dtype(op, a.dtype)), layout
 
     def reduce_axes_into(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int], out: CudaRaw, lo: Layout):
+        if out.dtype != self.redop_out_dtype(op, a.dtype):
+            raise RstsrCudaError(6, f"DTypeMismatch: {op} of {a.dtype} writes {self.redop_out_dtype(op, a.dtype)}, "
+                                    f"output storage is {out.dtype}")
         arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])
         check(_ffi.lib().rc_reduce_axes_into(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
                                              arr, len(axes), out.ptr, byref(lo.to_c())))
@@ -524,6 +595,23 @@ class Comm:
     def all_reduce(self, op: str, buf: CudaRaw, count: Optional[int] = None):
         check(_ffi.lib().rc_comm_all_reduce(self._handle, _ffi.REDOPS[op], dtype_code(buf.dtype), buf.ptr,
                                             buf.len if count is None else count))
+
+    def info(self) -> Tuple[int, int, bool]:
+        """(nranks, rank, peer_window): peer_window = results up to 256 KiB are combined by the one-kernel NVLink
+        exchange instead of ncclAllReduce."""
+        n, r, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(_ffi.lib().rc_comm_info(self._handle, byref(n), byref(r), byref(p)))
+        return n.value, r.value, bool(p.value)
+
+    def reduce_axes_sharded(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int], n_reduced_global: int,
+                            out: CudaRaw, lo: Layout):
+        """`*_axes` of a tensor whose SHARDED axis is reduced: `la` is this rank's shard, (out, lo) the full output."""
+        if out.dtype != a.dtype:
+            raise RstsrCudaError(6, "DTypeMismatch: sharded reductions write the element type")
+        arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])
+        check(_ffi.lib().rc_reduce_axes_sharded(self.device._handle, self._handle, _ffi.REDOPS[op], dtype_code(a.dtype),
+                                                a.ptr, byref(la.to_c()), arr, len(axes), int(n_reduced_global), out.ptr,
+                                                byref(lo.to_c())))
 
     def reduce_all_sharded(self, op: str, a: CudaRaw, la: Layout, n_global: int):
         out = np.empty(1, dtype=a.dtype)

@@ -85,6 +85,8 @@ def plan_reduce(layout: Layout, axes: Optional[Sequence[int]], op: str, nranks: 
     if kept_axis is not None and layout.shape[kept_axis] >= nranks:
         return ReducePlan(kept_axis, False, None, None)
     ax = outermost_axis(layout)
+    if ax is None:  # nothing to split (every extent <= 1): the operand is replicated, a collective would count it nranks times
+        return ReducePlan(None, False, None, None)
     return ReducePlan(ax, True, comb, div)
 
 

@@ -277,12 +277,8 @@ class Tensor:
             return self._with(view)
         target = Layout.contig(shape, order)
         raw = dev.uninit_impl(self.dtype, max(target.size, 1))
-        saved = dev.default_order()
-        dev.set_default_order(order)  # reshape.rs:155-162: pairing order = the requested order
-        try:
-            dev.assign_arbitary_uninit(raw, target, self.raw, self.layout)
-        finally:
-            dev.set_default_order(saved)
+        # reshape.rs:155-162: pairing order = the requested order, passed explicitly (the handle may be shared)
+        dev.assign_arbitary_uninit(raw, target, self.raw, self.layout, order)
         return Tensor(raw, target)
 
     into_shape = reshape
@@ -308,6 +304,7 @@ class Tensor:
         out_dtype = dev.binop_out_dtype(op, self.dtype)
         if isinstance(other, Tensor):
             a, b = (other, self) if reverse else (self, other)
+            out_dtype = dev.binop_out_dtype_ex(op, a.dtype, b.dtype)  # promotion when the operand types differ
             if not a.device.same_device(b.device):
                 raise _ffi.RstsrCudaError(5, "DeviceMismatch")
             la_b, lb_b = broadcast_layout(a.layout, b.layout, order)
@@ -320,13 +317,18 @@ class Tensor:
             raw = dev.uninit_impl(out_dtype, lc.bounds_index()[1])
             dev.op_mutc_refa_refb(op, raw, lc, a.raw, la_b, b.raw, lb_b)
             return Tensor(raw, lc)
-        # scalar operand (op_binary_arithmetic.rs:676-677, 746): layout_for_array_copy(K)
+        # scalar operand (op_binary_arithmetic.rs:676-677, 746): layout_for_array_copy(K).  The scalar has the tensor's
+        # element type, except a float scalar against an integer tensor, which is an f64 operand (promoted pair).
+        st = self.dtype
+        if isinstance(other, (float, np.floating)) and self.dtype.kind in "iub":
+            st = np.dtype(np.float64)
+        out_dtype = dev.binop_out_dtype_ex(op, *((st, self.dtype) if reverse else (self.dtype, st)))
         lc = layout_for_array_copy(self.layout, _ffi.ITER_K, order)
         raw = dev.uninit_impl(out_dtype, lc.bounds_index()[1])
         if reverse:
-            dev.op_mutc_numa_refb(op, raw, lc, other, self.raw, self.layout)
+            dev.op_mutc_numa_refb(op, raw, lc, other, self.raw, self.layout, a_dtype=st)
         else:
-            dev.op_mutc_refa_numb(op, raw, lc, self.raw, self.layout, other)
+            dev.op_mutc_refa_numb(op, raw, lc, self.raw, self.layout, other, b_dtype=st)
         return Tensor(raw, lc)
 
     def consume(self, op: str, other: "Tensor", reverse: bool = False) -> "Tensor":
@@ -585,6 +587,22 @@ def allclose(a: Tensor, b: Tensor, rtol: float = 1.0e-5, atol: float = 1.0e-8, e
         raise _ffi.RstsrCudaError(5, "DeviceMismatch")
     la_b, lb_b = broadcast_layout(a.layout, b.layout, dev.default_order())
     return dev.allclose_all(a.raw, la_b, b.raw, lb_b, rtol, atol, equal_nan)
+
+
+def isclose(a: Tensor, b: Tensor, rtol: float = 1.0e-5, atol: float = 1.0e-8, equal_nan: bool = False) -> Tensor:
+    """rt::isclose(a, b, args): elementwise OpIsCloseAPI (rstsr-core/src/operators/ops/op_ternary_common.rs:59-102);
+    output layout by the rule of the other binary-function ops (tensor/operators/op_binary_common.rs:79-93)."""
+    dev = a.device
+    if not dev.same_device(b.device):
+        raise _ffi.RstsrCudaError(5, "DeviceMismatch")
+    order = dev.default_order()
+    la_b, lb_b = broadcast_layout(a.layout, b.layout, order)
+    l1 = layout_for_array_copy(la_b, _ffi.ITER_K, order)
+    l2 = layout_for_array_copy(lb_b, _ffi.ITER_K, order)
+    lc = l1 if l1.same_as(l2) else Layout.contig(la_b.shape, order)
+    raw = dev.uninit_impl(np.bool_, max(lc.bounds_index()[1], 1))
+    dev.isclose(raw, lc, a.raw, la_b, b.raw, lb_b, rtol, atol, equal_nan)
+    return Tensor(raw, lc)
 
 
 # ---- creation from tensors: compositions of OpAssignAPI (rstsr-core/src/tensor/creation_from_tensor.rs) ----
