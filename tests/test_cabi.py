@@ -63,3 +63,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_rust_ffi_block_is_generated_from_the_header():
+    """crates-device/rstsr-cuda/src/ffi.rs must equal what scripts/gen_rust_ffi.py derives from include/rstsr_cuda.h,
+    and declare exactly the symbols the ctypes stub binds (header == ctypes stub == Rust extern block)."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(root, "scripts", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    committed = open(os.path.join(root, "crates-device", "rstsr-cuda", "src", "ffi.rs")).read()
+    assert committed == gen.generate(), "run `python scripts/gen_rust_ffi.py` after changing the header"
+    from rstsr_b200 import _ffi
+    assert set(re.findall(r"pub fn (rc_\w+)\(", committed)) == set(_ffi.SIGNATURES)
