@@ -364,10 +364,13 @@ def run_product(args, rank, local_rank, world):
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        step(record=True)
+        step()                      # the headline region carries no per-op events (8 event records cost ~16 us a step)
     t1.record()
     sync_all()
     launches = dev.launch_count() - launches0
+    for _ in range(args.steps):     # attribution pass: the same K steps again, each op bracketed by events
+        step(record=True)
+    sync_all()
     elapsed = torch.tensor([t0.elapsed_time(t1) * 1e-3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
@@ -394,17 +397,24 @@ def run_product(args, rank, local_rank, world):
                             if world > 1 else "rel 1e-12 vs torch")}
 
     peak, peak_kind = measured_peak()
-    per_op = {}
+    per_op = {"_note": "separate attribution pass of the same K steps with CUDA events around every op (max over ranks); "
+                       "an op's time includes the write-back of its predecessor's dirty L2 lines"}
     for k, pairs in ev.items():
         ms = sum(e0.elapsed_time(e1) for e0, e1 in pairs) / max(len(pairs), 1)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        ms_min = ms
         if dist is not None:
+            tmin = t.clone()
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            ms_min = float(tmin.item())
         ms = float(t.item())
         nbytes = {"cfg1": BYTES_CFG1, "cfg2": BYTES_CFG2, "cfg3_rows": BYTES_CFG3, "cfg3_cols": BYTES_CFG3}[k]
         gbs = nbytes / (ms * 1e-3) / 1e9
         per_op[k] = {"us": round(ms * 1e3, 1), "gbs": round(gbs, 1), "frac_measured": round(gbs / peak, 4),
                      "frac_8TBs": round(gbs / 8000, 4), "check": checks[k]}
+        if dist is not None:  # fastest rank: the spread is GPU-to-GPU variation (no collective in cfg1 / cfg2 / cfg3_rows)
+            per_op[k]["us_fastest_rank"] = round(ms_min * 1e3, 1)
     del a1, b1, c1, src2, dst2, m3, o3r, o3c, probe, ref_r, ref_c
 
     # ---- the other named configurations, same process, same rules ----
@@ -605,6 +615,20 @@ def run_per_config(args, rank, world, dev, comm, rt, np, torch, dist, peak):
         del x
     else:
         rows["cfg5"] = {"skipped": f"{per * 8 >> 30} GiB per rank does not fit the free {free_b >> 30} GiB"}
+
+    # ---- the exchange step alone: ranks in lock-step, 200 back-to-back all-reduces of the cfg3 partial (128 KiB) ----
+    if comm is not None:
+        buf = torch.rand(N3, generator=g, **f64)
+        rb = wrap(buf)
+        had_peer = comm.info()[2]
+        for label, enable in (("peer window", True), ("ncclAllReduce", False)):
+            if enable and not had_peer:
+                continue
+            comm.set_peer_window(enable)   # same call on every rank, between the same two collectives
+            sec = timeit(lambda: comm.all_reduce("max", rb), n=200, warmup=10)
+            rows[f"exchange only: all-reduce of 16384 f64, {label}"] = {"us": round(sec * 1e6, 2), "scaling": "latency",
+                                                                        "check": "see tests/test_gpu_multi.py"}
+        comm.set_peer_window(had_peer)
     return rows
 
 

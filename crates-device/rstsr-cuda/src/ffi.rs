@@ -367,6 +367,25 @@ extern "C" {
         out_dev: *mut c_void,
         lo: *const rc_layout,
     ) -> c_int;
+    pub fn rc_reduce_unraveled_arg_all(
+        dev: *mut rc_device,
+        op: c_int,
+        dtype: c_int,
+        a: *const c_void,
+        la: *const rc_layout,
+        index_out: *mut i64,
+    ) -> c_int;
+    pub fn rc_reduce_unraveled_arg_axes(
+        dev: *mut rc_device,
+        op: c_int,
+        dtype: c_int,
+        a: *const c_void,
+        la: *const rc_layout,
+        axes: *const i64,
+        naxes: c_int,
+        out_dev: *mut *mut c_void,
+        lo_out: *mut rc_layout,
+    ) -> c_int;
     pub fn rc_vecdot(
         dev: *mut rc_device,
         dtype: c_int,
@@ -432,6 +451,7 @@ extern "C" {
     ) -> c_int;
     pub fn rc_comm_destroy(comm: *mut rc_comm) -> c_int;
     pub fn rc_comm_info(comm: *const rc_comm, nranks: *mut c_int, rank: *mut c_int, peer_window: *mut c_int) -> c_int;
+    pub fn rc_comm_set_peer_window(comm: *mut rc_comm, enable: c_int) -> c_int;
     pub fn rc_comm_all_reduce(
         comm: *mut rc_comm,
         op: c_int,

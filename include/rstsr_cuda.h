@@ -377,6 +377,19 @@ int rc_reduce_axes(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, c
 int rc_reduce_axes_into(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la,
                         const int64_t *axes, int naxes, void *out_dev, const rc_layout *lo);
 
+/* OpUnraveledArgMin/MaxAPI (rstsr-core/src/operators/reduction.rs:35-55; reduce_*_unraveled_arg_cpu_serial,
+ * rstsr-native-impl/src/cpu_serial/reduction.rs:421-529): the position of the first extreme element as an index TUPLE.
+ *   _all:  index_out[0 .. la->ndim) = the position within `la` (host memory; synchronises).
+ *   _axes: the callee allocates u64[lo_out->size()][naxes] (free with rc_free): for the output element that lives at
+ *          element offset m of lo_out (layout as rc_layout_for_reduce), entries m * naxes + k, k < naxes, are its
+ *          position within the REDUCED axes in the order given (the reference returns Vec<IxD> elements; a device
+ *          buffer holds them as fixed-length u64 tuples).
+ * op is RC_ARGMIN or RC_ARGMAX; a zero-size input is RC_ERR_INVALID_LAYOUT as in the reference. */
+int rc_reduce_unraveled_arg_all(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la,
+                                int64_t *index_out);
+int rc_reduce_unraveled_arg_axes(rc_device *dev, rc_redop op, rc_dtype dtype, const void *a, const rc_layout *la,
+                                 const int64_t *axes, int naxes, void **out_dev, rc_layout *lo_out);
+
 /* ------------------------------------------------------------------------------------------
  * Binary reductions: two input streams folded in one pass.
  *   rc_vecdot:       DeviceVecdotAPI::vecdot (rstsr-core/src/device_cpu_serial/linalg/vecdot.rs:4-29,
@@ -436,6 +449,10 @@ int rc_comm_destroy(rc_comm *comm);
  * disables the window (NCCL only); RC_COMM_TIMEOUT_S bounds the in-kernel wait for a lost rank (default 120 s,
  * then the kernel traps instead of hanging the job).  Any out pointer may be NULL. */
 int rc_comm_info(const rc_comm *comm, int *nranks, int *rank, int *peer_window);
+/* Switch the peer window off (NCCL for every size) or back on.  COLLECTIVE in spirit: every rank must make the same
+ * call between the same two reductions, otherwise the next reduction pairs a window kernel with an NCCL kernel and
+ * times out.  Enabling fails with RC_ERR_DEVICE when the window could not be mapped at rc_comm_init_rank. */
+int rc_comm_set_peer_window(rc_comm *comm, int enable);
 /* in-place all-reduce of `count` elements with the reduction's combiner (sum/prod/max/min; mean = sum,
  * the caller divides by the global count via rc_op_muta_numb) on the device's stream.  All element types
  * (16-bit integers have no NCCL type: they go through the window, or widened to 32 bits above its size). */

@@ -130,6 +130,7 @@ SIGNATURES = {
     "rc_comm_destroy": (c_int, [_P]),
     "rc_comm_all_reduce": (c_int, [_P, c_int, c_int, _P, c_size_t]),
     "rc_reduce_all_sharded": (c_int, [_P, _P, c_int, c_int, _P, _L, c_int64, _P]),
+    "rc_comm_set_peer_window": (c_int, [_P, c_int]),
     "rc_comm_info": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "rc_reduce_axes_sharded": (c_int, [_P, _P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, c_int64, _P, _L]),
     "rc_device_numa_node": (c_int, [_P, POINTER(c_int)]),
@@ -140,6 +141,8 @@ SIGNATURES = {
     "rc_op_mutc_refa_refb_ex": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, _L, c_int, _P, _L]),
     "rc_op_mutc_refa_numb_ex": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, _L, c_int, _P]),
     "rc_op_mutc_numa_refb_ex": (c_int, [_P, c_int, c_int, _P, _L, c_int, _P, c_int, _P, _L]),
+    "rc_reduce_unraveled_arg_all": (c_int, [_P, c_int, c_int, _P, _L, POINTER(c_int64)]),
+    "rc_reduce_unraveled_arg_axes": (c_int, [_P, c_int, c_int, _P, _L, POINTER(c_int64), c_int, POINTER(_P), _L]),
     "rc_isclose": (c_int, [_P, c_int, _P, _L, _P, _L, _P, _L, c_double, c_double, c_int]),
 }
 

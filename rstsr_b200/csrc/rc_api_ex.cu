@@ -140,6 +140,24 @@ void status(int st) {
     if (st != RC_OK) raise((rc_status)st, rc_last_error());
 }
 
+// flat row-major index within `shape` -> index tuple, one thread per output element
+struct UnravelDesc {
+    int n;
+    int64_t shape[RC_MAX_NDIM];
+};
+__global__ void unravel_kernel(const __grid_constant__ UnravelDesc d, const uint64_t *__restrict__ flat,
+                               uint64_t *__restrict__ out, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t idx = flat[i];
+    for (int k = d.n - 1; k >= 0; --k) {
+        const uint64_t e = (uint64_t)d.shape[k];
+        const uint64_t q = idx / e;
+        out[i * d.n + k] = idx - q * e;
+        idx = q;
+    }
+}
+
 // ---- NUMA-bound pinned buffers ----
 std::mutex g_numa_mu;
 std::map<void *, size_t> g_numa_blocks;  // mmap'ed + cudaHostRegister'ed
@@ -308,6 +326,56 @@ int rc_isclose(rc_device *dev, rc_dtype t, void *c, const rc_layout *lc_, const 
         EwArgs args;
         args.c = c; args.a = a; args.b = b; args.params = &p;
         run_isclose(dev, t, cn, args);
+    });
+}
+
+int rc_reduce_unraveled_arg_all(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const rc_layout *la_,
+                                int64_t *index_out) {
+    return guard([&] {
+        RC_CHECK(op == RC_ARGMIN || op == RC_ARGMAX, RC_ERR_INVALID_VALUE, "unraveled arg takes RC_ARGMIN or RC_ARGMAX");
+        Layout la = from_c(la_);
+        RC_CHECK(index_out != nullptr || la.ndim() == 0, RC_ERR_INVALID_VALUE, "null index_out");
+        uint64_t flat = 0;
+        status(rc_reduce_all(dev, op, t, a, la_, &flat));  // row-major position over all axes; first occurrence wins
+        for (int k = la.ndim() - 1; k >= 0; --k) {
+            const uint64_t e = (uint64_t)la.shape[k];
+            index_out[k] = (int64_t)(flat % e);
+            flat /= e;
+        }
+    });
+}
+
+int rc_reduce_unraveled_arg_axes(rc_device *dev, rc_redop op, rc_dtype t, const void *a, const rc_layout *la_,
+                                 const int64_t *axes_, int naxes, void **out_dev, rc_layout *lo_out) {
+    return guard([&] {
+        DeviceGuard g(dev);
+        RC_CHECK(op == RC_ARGMIN || op == RC_ARGMAX, RC_ERR_INVALID_VALUE, "unraveled arg takes RC_ARGMIN or RC_ARGMAX");
+        RC_CHECK(out_dev && lo_out, RC_ERR_INVALID_VALUE, "null out");
+        *out_dev = nullptr;
+        Layout la = from_c(la_);
+        std::vector<int> axes = normalize_axes(axes_, naxes, la.ndim());
+        void *flat = nullptr;
+        status(rc_reduce_axes(dev, op, t, a, la_, axes_, naxes, &flat, lo_out));  // u64 positions, layout lo_out
+        Layout lo = from_c(lo_out);
+        int64_t mn = 0, mx = 0;
+        bounds_index(lo, &mn, &mx);
+        const int64_t count = std::max<int64_t>(mx, 1);  // rc_layout_for_reduce layouts are dense from offset 0
+        void *out = nullptr;
+        cudaError_t e = cudaMallocAsync(&out, (size_t)count * std::max(naxes, 1) * sizeof(uint64_t), dev->stream);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(flat, dev->stream);
+            raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        }
+        if (naxes > 0) {
+            UnravelDesc d;
+            d.n = naxes;
+            for (int k = 0; k < naxes; ++k) d.shape[k] = la.shape[axes[k]];
+            unravel_kernel<<<(unsigned)((count + 255) / 256), 256, 0, dev->stream>>>(
+                d, static_cast<const uint64_t *>(flat), static_cast<uint64_t *>(out), count);
+            after_launch(dev, "unravel_kernel");
+        }
+        cudaFreeAsync(flat, dev->stream);
+        *out_dev = out;
     });
 }
 

@@ -533,6 +533,16 @@ int rc_comm_info(const rc_comm *comm, int *nranks, int *rank, int *peer_window) 
     });
 }
 
+int rc_comm_set_peer_window(rc_comm *comm, int enable) {
+    return guard([&] {
+        RC_CHECK(comm != nullptr, RC_ERR_INVALID_VALUE, "null comm");
+        std::lock_guard<std::mutex> lock(comm->mu);
+        if (enable) RC_CHECK(comm->win_local != nullptr && comm->win[comm->rank] != nullptr, RC_ERR_DEVICE,
+                             "the peer window was not mapped when the communicator was created");
+        comm->peer = enable != 0;
+    });
+}
+
 int rc_comm_all_reduce(rc_comm *comm, rc_redop op, rc_dtype t, void *buf, size_t count) {
     return guard([&] {
         RC_CHECK(comm != nullptr, RC_ERR_INVALID_VALUE, "null comm");

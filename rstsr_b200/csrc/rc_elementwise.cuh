@@ -20,6 +20,8 @@
 
 namespace rc {
 
+template <class T> struct FIdentity;  // rc_functors.cuh (the bit-moving copy the TMA-engine tile kernel serves)
+
 enum OperandMode : int {
     MODE_MEM = 0,    // read through the operand's strides
     MODE_CONST = 1,  // host scalar passed in the kernel parameters (`numa` / `numb` variants, fill)
@@ -382,6 +384,26 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
     }
 }
 
+}  // namespace rc
+#include "rc_tile_bulk.cuh"
+#include "rc_tile_narrow.cuh"
+namespace rc {
+
+// RC_TILE_NARROW=0 sends 1- / 2-byte permuted copies back to the one-element-per-lane tile kernels (experiments)
+inline bool tile_narrow_enabled() {
+    static bool v = [] { const char *e = getenv("RC_TILE_NARROW"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+// default choice between the two tile kernels (filled in from the measurement: profiles/r02_tile_bulk.md)
+inline bool tile_bulk_default(uint32_t total_tiles, int sm_count) { return false && total_tiles >= 8u * (uint32_t)sm_count; }
+
+// RC_TILE_BULK = 0 / 1 forces the TMA copy kernel off / on where it is eligible (default: see tile_bulk_default)
+inline int tile_bulk_mode() {
+    static int v = [] { const char *e = getenv("RC_TILE_BULK"); return e ? atoi(e) : -1; }();
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // rectangular tile kernel: one of X / Y is short and the other long.  The square kernel above
 // would leave most of its 64 x 64 slots predicated off (nx = 17: 27 % of the lanes carry data), so here the tile is
@@ -638,7 +660,12 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
     constexpr int NIN = F::NIN;
     constexpr size_t maxsz = sizeof(TO) > sizeof(TA) ? (sizeof(TO) > sizeof(TB) ? sizeof(TO) : sizeof(TB))
                                                      : (sizeof(TA) > sizeof(TB) ? sizeof(TA) : sizeof(TB));
-    constexpr int V = ALLOW_VEC ? (int)(16 / maxsz) : 1;
+    constexpr size_t minsz = sizeof(TO) < sizeof(TA) ? (sizeof(TO) < sizeof(TB) ? sizeof(TO) : sizeof(TB))
+                                                     : (sizeof(TA) < sizeof(TB) ? sizeof(TA) : sizeof(TB));
+    // elements per pack: 16 bytes of the widest type -- or 32 bytes (256-bit LDG / STG) when the operand types differ in
+    // size (casts, comparisons): the narrow side would otherwise move 2-4 bytes per thread and instruction
+    // (u8 -> f32 measured 3.7 TB/s with 4-byte loads)
+    constexpr int V = ALLOW_VEC ? (int)((maxsz != minsz ? 32 : 16) / maxsz) : 1;
 
     TO *pc = static_cast<TO *>(args.c) + c.base[0];
     const TA *pa = nullptr;
@@ -780,6 +807,72 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                                                                                                     tm_b, ka, kb, prm);
                         after_launch(dev, "ew_tile_rect_kernel");
                         return;
+                    }
+                }
+                // 1- / 2-byte permuted COPY: word-granular tile (rc_tile_narrow.cuh)
+                if constexpr (NIN == 1 && (std::is_same<F, FIdentity<uint8_t>>::value || std::is_same<F, FIdentity<uint16_t>>::value)) {
+                    constexpr int ESZ = (int)sizeof(TO), E = 4 / ESZ;
+                    bool ok = tile_narrow_enabled() && tm_a == TILE_STAGED && t.sx[0] == 1 && t.sy[1] == 1 && t.nx % E == 0 &&
+                              t.ny % E == 0 && (int64_t)t.nx * ESZ >= 64 && (int64_t)t.ny * ESZ >= 64 && t.sx[1] % E == 0 &&
+                              t.sy[0] % E == 0 && reinterpret_cast<uintptr_t>(pc) % 4 == 0 && reinterpret_cast<uintptr_t>(pa) % 4 == 0;
+                    for (int i = 0; i < t.nbatch && ok; ++i) ok = t.bstride[0][i] % E == 0 && t.bstride[1][i] % E == 0;
+                    if (ok) {
+                        NarrowDesc nd;
+                        std::memset(&nd, 0, sizeof(nd));
+                        nd.nx = t.nx;
+                        nd.ny = t.ny;
+                        nd.tiles_x = (t.nx + NW_WORDS_X * E - 1) / (NW_WORDS_X * E);
+                        nd.tiles_y = (t.ny + NW_WORDS_Y * E - 1) / (NW_WORDS_Y * E);
+                        nd.div_tx = FastDiv(nd.tiles_x);
+                        nd.div_ty = FastDiv(nd.tiles_y);
+                        nd.nbatch = t.nbatch;
+                        int64_t nb2 = 1;
+                        for (int i = 0; i < t.nbatch; ++i) {
+                            nd.bdiv[i] = t.bdiv[i];
+                            nd.bstride_c[i] = t.bstride[0][i];
+                            nd.bstride_a[i] = t.bstride[1][i];
+                            nb2 *= t.bdiv[i].d;
+                        }
+                        nd.sx_a = t.sx[1];
+                        nd.sy_c = t.sy[0];
+                        const int64_t tiles = (int64_t)nd.tiles_x * nd.tiles_y * nb2;
+                        if (tiles < (1ll << 31)) {
+                            nd.total_tiles = (uint32_t)tiles;
+                            ew_tile_narrow_kernel<ESZ><<<nd.total_tiles, NW_WARPS * 32, 0, dev->stream>>>(
+                                nd, reinterpret_cast<unsigned char *>(pc), reinterpret_cast<const unsigned char *>(pa));
+                            after_launch(dev, "ew_tile_narrow_kernel");
+                            return;
+                        }
+                    }
+                }
+                // 8-byte permuted COPY of whole 64 x 64 tiles: the TMA kernel (rc_tile_bulk.cuh) where the tensor maps exist
+                if constexpr (NIN == 1 && std::is_same<F, FIdentity<uint64_t>>::value) {
+                    const int bulk = tile_bulk_mode();
+                    if ((bulk == 1 || (bulk < 0 && tile_bulk_default(t.total_tiles, dev->sm_count))) && tm_a == TILE_STAGED &&
+                        t.nx % BK_T == 0 && t.ny % BK_T == 0 && t.sx[0] == 1 && t.sy[1] == 1 && t.nbatch <= 3) {
+                        CUtensorMap map_src, map_dst;
+                        TmaTileDesc td;
+                        std::memset(&td, 0, sizeof(td));
+                        td.total_tiles = t.total_tiles;
+                        td.nbatch = t.nbatch;
+                        td.div_ty = t.div_ty;
+                        td.div_tx = t.div_tx;
+                        std::vector<TmaDim> sd, dd;
+                        sd.push_back(TmaDim{t.nx, t.sx[1], (uint32_t)BK_T, 0});
+                        dd.push_back(TmaDim{t.ny, t.sy[0], (uint32_t)BK_T, 0});
+                        for (int i = 0; i < t.nbatch; ++i) {
+                            td.bdiv[i] = t.bdiv[i];
+                            sd.push_back(TmaDim{t.bdiv[i].d, t.bstride[1][i], 1u, 1 + i});
+                            dd.push_back(TmaDim{t.bdiv[i].d, t.bstride[0][i], 1u, 1 + i});
+                        }
+                        if (tma_make_map(&map_src, const_cast<TA *>(pa), t.ny, (uint32_t)BK_T, sd, td.src_slot, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+                            tma_make_map(&map_dst, pc, t.nx, 16u, dd, td.dst_slot, CU_TENSOR_MAP_SWIZZLE_128B)) {
+                            RC_CUDA(cudaFuncSetAttribute(ew_tile_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
+                            const uint32_t grid = std::min<uint32_t>(t.total_tiles, (uint32_t)dev->sm_count);
+                            ew_tile_tma_kernel<0><<<grid, BK_THREADS, BK_SMEM, dev->stream>>>(map_src, map_dst, td);
+                            after_launch(dev, "ew_tile_tma_kernel");
+                            return;
+                        }
                     }
                 }
                 if (square_x_ok && t.ny >= (uint32_t)tile_min_y(esz_staged)) {

@@ -512,6 +512,25 @@ class DeviceCuda:
         check(_ffi.lib().rc_reduce_axes_into(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr, byref(la.to_c()),
                                              arr, len(axes), out.ptr, byref(lo.to_c())))
 
+    def unraveled_arg_all(self, op: str, a: CudaRaw, la: Layout) -> Tuple[int, ...]:
+        """OpUnraveledArgMin/MaxAPI::unraveled_arg*_all (operators/reduction.rs:35-55): index tuple within `la`."""
+        out = (ctypes.c_int64 * max(la.ndim, 1))()
+        check(_ffi.lib().rc_reduce_unraveled_arg_all(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr,
+                                                     byref(la.to_c()), out))
+        return tuple(int(out[i]) for i in range(la.ndim))
+
+    def unraveled_arg_axes(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int]) -> Tuple[CudaRaw, Layout]:
+        """unraveled_arg*_axes: u64 tuples [lo.size][naxes] (position within the reduced axes, in the order given) and
+        the layout `lo` of the output elements."""
+        arr = (ctypes.c_int64 * max(len(axes), 1))(*[int(x) for x in axes])
+        p = ctypes.c_void_p()
+        lo = CLayout()
+        check(_ffi.lib().rc_reduce_unraveled_arg_axes(self._handle, _ffi.REDOPS[op], dtype_code(a.dtype), a.ptr,
+                                                      byref(la.to_c()), arr, len(axes), byref(p), byref(lo)))
+        layout = Layout.from_c(lo)
+        n = max(layout.bounds_index()[1], 1) * max(len(axes), 1)
+        return CudaRaw(self, p.value, n, np.uint64), layout
+
     # ---- binary reductions ----
     def vecdot(self, c: CudaRaw, lc: Layout, a: CudaRaw, la: Layout, b: CudaRaw, lb: Layout, axes_a: Sequence[int],
                axes_b: Sequence[int]):
@@ -602,6 +621,10 @@ class Comm:
         n, r, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         check(_ffi.lib().rc_comm_info(self._handle, byref(n), byref(r), byref(p)))
         return n.value, r.value, bool(p.value)
+
+    def set_peer_window(self, enable: bool):
+        """Every rank must make the same call at the same point (see rc_comm_set_peer_window)."""
+        check(_ffi.lib().rc_comm_set_peer_window(self._handle, 1 if enable else 0))
 
     def reduce_axes_sharded(self, op: str, a: CudaRaw, la: Layout, axes: Sequence[int], n_reduced_global: int,
                             out: CudaRaw, lo: Layout):

@@ -245,3 +245,25 @@ def test_change_device_between_handles(dev):
     finally:
         for tgt in targets:
             tgt.close()
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.bool_, np.int16, np.uint16])
+def test_narrow_permuted_copies(dev, dtype):
+    """1- / 2-byte permuted copies take the word-granular tile (rc_tile_narrow.cuh) when extents and strides allow,
+    the one-element-per-lane kernels otherwise: both must be bit-exact, partial tiles and batches included."""
+    rng = np.random.default_rng(seed_of(("narrow", np.dtype(dtype).name)))
+    cases = [((256, 384), (1, 0)), ((132, 260), (1, 0)), ((130, 258), (1, 0)), ((131, 257), (1, 0)), ((5, 200, 136), (0, 2, 1)),
+             ((72, 3, 520), (2, 1, 0)), ((3, 140, 2, 148), (2, 3, 0, 1)), ((64, 64), (1, 0)), ((1000, 12), (1, 0)), ((12, 1000), (1, 0))]
+    for shape, perm in cases:
+        n = int(np.prod(shape))
+        a = rng.integers(0, 2 if dtype == np.bool_ else 120, n).astype(dtype)
+        la = L.c_contig_layout(list(shape)).transpose(list(perm))
+        t = rt.Tensor(upload(dev, a), P(la)).to_contig(rt.ROW_MAJOR)
+        want = np.ascontiguousarray(a.reshape(shape).transpose(perm))
+        assert np.array_equal(t.to_numpy(), want), (dtype, shape, perm)
+        # a sliced source (offset, pitch not a multiple of 4 bytes in general)
+        sl = la.narrow(0, slice(1, None)).narrow(1, slice(2, None))
+        t2 = rt.Tensor(upload(dev, a), P(sl)).to_contig(rt.ROW_MAJOR)
+        idx = [slice(None)] * len(shape)
+        v = a.reshape(shape).transpose(perm)[1:, 2:]
+        assert np.array_equal(t2.to_numpy(), np.ascontiguousarray(v)), (dtype, shape, perm, "sliced")

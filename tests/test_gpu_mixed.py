@@ -224,3 +224,32 @@ def test_same_device_needs_same_stream(dev):
         assert np.array_equal((x + moved).to_numpy(), np.full(4, 2.0))
     finally:
         other.close()
+
+
+@pytest.mark.parametrize("op", ["argmin", "argmax"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32])
+def test_unraveled_arg(dev, op, dtype):
+    """OpUnraveledArgMin/MaxAPI (operators/reduction.rs:35-55): the index TUPLE of the first extreme element -- within
+    the tensor for `_all`, within the reduced axes (in the order given) for `_axes`
+    (reduce_axes_unraveled_arg_cpu_serial, cpu_serial/reduction.rs:479-529)."""
+    rng = np.random.default_rng(seed_of(("unravel", op, np.dtype(dtype).name)))
+    shape = (7, 9, 11)
+    a = rand_data(rng, int(np.prod(shape)), dtype)
+    a[rng.integers(0, a.size, 40)] = a.max() if op == "argmax" else a.min()   # ties: the first occurrence wins
+    for la in (L.c_contig_layout(list(shape)), L.c_contig_layout(list(shape)).transpose([2, 0, 1]),
+               L.f_contig_layout(list(shape)).narrow(1, slice(None, None, -1))):
+        raw = upload(dev, a)
+        flat = int(oracle.reduce_ext(op, a, la))
+        assert dev.unraveled_arg_all(op, raw, P(la)) == tuple(int(i) for i in np.unravel_index(flat, la.shape))
+        for axes in ([0], [2, 0], [1, 2], [-1], [0, 1, 2]):
+            ref, lref = oracle.reduce_ext(op, a, la, axes)
+            tuples, lo = dev.unraveled_arg_axes(op, raw, P(la), axes)
+            assert (lo.shape, lo.stride, lo.offset) == (tuple(lref.shape), tuple(lref.stride), lref.offset)
+            got = dev.to_cpu_vec(tuples).reshape(-1, len(axes))
+            red_shape = tuple(la.shape[ax % 3] for ax in axes)
+            want_flat = np.asarray(ref).reshape(-1)          # u64 positions, memory order of lref
+            want = np.stack(np.unravel_index(want_flat.astype(np.int64), red_shape), axis=-1)
+            assert np.array_equal(got[:want.shape[0]], want), (op, dtype, axes)
+    with pytest.raises(rt.RstsrCudaError) as e:
+        dev.unraveled_arg_all(op, upload(dev, np.zeros(1, dtype=dtype)), rt.Layout((0, 3), (3, 1)))
+    assert e.value.kind == "InvalidLayout"
