@@ -238,6 +238,74 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_rows_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// outer kernel: WRITE-ONLY broadcast ops c[i, j] = f(u[i], v[j]) (outer sum / product, `a[:, None] * b[None, :]`).
+// One operand is constant along the rows (kept in registers: packs of v, or a host scalar), the other is one scalar per
+// row (stride 0 along dim 0).  A CTA owns a 1024-pack chunk of dim 0 and walks R rows: the kept packs are loaded once,
+// the row scalar of row r + 1 is fetched while row r is computed and stored, so the loop body is FADD/FMUL + STG only.
+// (The flat kernel spent 98 instructions per 16-byte pack on this shape -- every operand mode materialised per slot --
+// and was issue-bound at 4.4 TB/s, profiles/r01_instruction_mix.md.)
+// SPL = 1: a is the row scalar, b is kept; SPL = 2: b is the row scalar, a is kept.
+// ---------------------------------------------------------------------------------------------
+constexpr int EW_OUTER_ROWS = 8;
+
+template <class F, int VEC, int SPL>
+__global__ void __launch_bounds__(EW_BLOCK) ew_outer_kernel(const __grid_constant__ EwRowsDesc d, typename F::TO *c,
+                                                            const typename F::TA *a, const typename F::TB *b,
+                                                            int mode_kept, EwConst<typename F::TA> ka,
+                                                            EwConst<typename F::TB> kb, ew_params_t<F> prm) {
+    using TA = typename F::TA;
+    using TB = typename F::TB;
+    using TO = typename F::TO;
+    using TK = typename std::conditional<SPL == 1, TB, TA>::type;  // kept operand
+    using TS = typename std::conditional<SPL == 1, TA, TB>::type;  // row scalar
+    constexpr int KS = SPL == 1 ? 2 : 1, SS = SPL == 1 ? 1 : 2;     // their slots in the descriptor
+    uint32_t rg, chunk;
+    d.div_chunks.divmod(blockIdx.x, rg, chunk);
+    const uint32_t q0 = rg * d.rows_per_cta;
+    const uint32_t rows = min(d.rows_per_cta, d.n1 - q0);
+    const uint32_t first = chunk * (EW_BLOCK * EW_UNROLL) + threadIdx.x;
+
+    TO *pc = c + ((int64_t)first * d.s0[0] + (int64_t)q0 * d.s1[0]);
+    const int64_t step_c = (int64_t)EW_BLOCK * d.s0[0], step_k = (int64_t)EW_BLOCK * d.s0[KS];
+    const TK *pk;
+    const TS *ps;
+    TK kconst;
+    if constexpr (SPL == 1) { pk = b + (int64_t)first * d.s0[2]; ps = a + (int64_t)q0 * d.s1[1]; kconst = kb.v; }
+    else                    { pk = a + (int64_t)first * d.s0[1]; ps = b + (int64_t)q0 * d.s1[2]; kconst = ka.v; }
+
+    bool ok[EW_UNROLL];
+    Pack<TK, VEC> vk[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        ok[u] = first + u * EW_BLOCK < d.n0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) vk[u].v[j] = kconst;
+        ld_stream_pred<TK, VEC>(vk[u], pk + u * step_k, ok[u] && mode_kept == MODE_MEM);
+    }
+    const int64_t ss = d.s1[SS];
+    TS cur = *ps;
+    for (uint32_t row = 0; row < rows; ++row) {
+        TS nxt = cur;
+        if (row + 1 < rows) nxt = ps[ss];  // every thread of the CTA reads the same word: one broadcast transaction
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            if (ok[u]) {
+                Pack<TO, VEC> r;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if constexpr (SPL == 1) r.v[j] = ew_apply<F>(cur, vk[u].v[j], prm);
+                    else r.v[j] = ew_apply<F>(vk[u].v[j], cur, prm);
+                }
+                st_stream<TO, VEC>(pc + u * step_c, r);
+            }
+        }
+        pc += d.s1[0];
+        ps += ss;
+        cur = nxt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // tile kernel.  X = canonical dim 0 (output stride 1), Y = the staged inputs' unit-stride dim.
 // ---------------------------------------------------------------------------------------------
 // Smallest extents that take the tile kernel (tuning knobs RC_TILE_MIN_X / RC_TILE_MIN_Y for experiments):
@@ -389,6 +457,11 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
 #include "rc_tile_narrow.cuh"
 namespace rc {
 
+// RC_EW_OUTER=0 keeps write-only outer ops on the flat kernel (experiments)
+inline bool outer_enabled() {
+    static bool v = [] { const char *e = getenv("RC_EW_OUTER"); return !(e && e[0] == '0'); }();
+    return v;
+}
 // RC_TILE_NARROW=0 sends 1- / 2-byte permuted copies back to the one-element-per-lane tile kernels (experiments)
 inline bool tile_narrow_enabled() {
     static bool v = [] { const char *e = getenv("RC_TILE_NARROW"); return !(e && e[0] == '0'); }();
@@ -911,6 +984,37 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
         if (vec_ok) {
             if (slot_a >= 0 && c.stride[slot_a][0] == 0) mode_a = MODE_SPLAT;
             if (slot_b >= 0 && c.stride[slot_b][0] == 0) mode_b = MODE_SPLAT;
+            // write-only outer op: one operand is a scalar per row, the other does not change from row to row
+            bool outer_done = false;
+            if constexpr (NIN == 2) {
+                if (c.ndim == 2 && c.shape[1] < (1ll << 31) && c.shape[1] >= 2 && outer_enabled()) {
+                    const bool row_a = mode_a == MODE_SPLAT && c.stride[slot_a][1] != 0;
+                    const bool row_b = mode_b == MODE_SPLAT && c.stride[slot_b][1] != 0;
+                    const bool kept_a = mode_a == MODE_CONST || (mode_a == MODE_MEM && c.stride[slot_a][1] == 0);
+                    const bool kept_b = mode_b == MODE_CONST || (mode_b == MODE_MEM && c.stride[slot_b][1] == 0);
+                    if ((row_a && kept_b) || (row_b && kept_a)) {
+                        EwRowsDesc rd;
+                        std::memset(&rd, 0, sizeof(rd));
+                        rd.n0 = (uint32_t)(c.shape[0] / V);
+                        rd.n1 = (uint32_t)c.shape[1];
+                        for (int k = 0; k < 3; ++k) {
+                            rd.s0[k] = stride_of(slots[k], 0) * V;
+                            rd.s1[k] = stride_of(slots[k], 1);
+                        }
+                        rd.rows_per_cta = EW_OUTER_ROWS;
+                        const uint32_t chunks = (rd.n0 + EW_BLOCK * EW_UNROLL - 1) / (EW_BLOCK * EW_UNROLL);
+                        rd.div_chunks = FastDiv(chunks);
+                        const int64_t g2 = ((int64_t)(rd.n1 + rd.rows_per_cta - 1) / rd.rows_per_cta) * chunks;
+                        if (g2 < (1ll << 31)) {
+                            if (row_a) ew_outer_kernel<F, V, 1><<<(unsigned)g2, EW_BLOCK, 0, dev->stream>>>(rd, pc, pa, pb, mode_b, ka, kb, prm);
+                            else ew_outer_kernel<F, V, 2><<<(unsigned)g2, EW_BLOCK, 0, dev->stream>>>(rd, pc, pa, pb, mode_a, ka, kb, prm);
+                            after_launch(dev, "ew_outer_kernel");
+                            outer_done = true;
+                        }
+                    }
+                }
+            }
+            if (outer_done) return;
             if (c.ndim == 1) {
                 ew_kernel<F, V, 1><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
             } else if (c.ndim == 2 && c.shape[0] / V >= 512 && c.shape[1] < (1ll << 31) &&

@@ -253,3 +253,29 @@ def test_unraveled_arg(dev, op, dtype):
     with pytest.raises(rt.RstsrCudaError) as e:
         dev.unraveled_arg_all(op, upload(dev, np.zeros(1, dtype=dtype)), rt.Layout((0, 3), (3, 1)))
     assert e.value.kind == "InvalidLayout"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int16])
+def test_outer_ops_take_both_operand_orders(dev, dtype):
+    """c[i, j] = u[i] op v[j] and v[j] op u[i] (ew_outer_kernel, SPL = 1 / 2): non-commutative ops pin the operand order;
+    odd row counts exercise the last partial CTA, row strides != 1 the scalar walk."""
+    rng = np.random.default_rng(seed_of(("outer", np.dtype(dtype).name)))
+    for n_rows, n_cols, ustep in ((37, 2048, 1), (8, 4096, 3), (1001, 1024, 1), (5, 64, 2)):
+        u = rand_data(rng, n_rows * ustep, dtype)
+        v = rand_data(rng, n_cols, dtype)
+        if np.dtype(dtype).kind != "f":
+            v[v == 0] = 1
+            u[u == 0] = 1
+        lu = L.Layout((n_rows, 1), (ustep, 1), 0)   # column vector, every ustep-th element
+        lv = L.c_contig_layout([n_cols])
+        tu, tv = rt.Tensor(upload(dev, u), P(lu)), rt.Tensor(upload(dev, v), P(lv))
+        uu = u[::ustep][:n_rows].reshape(n_rows, 1)
+        for op, fn in (("sub", np.subtract), ("add", np.add), ("mul", np.multiply)):
+            got = tu.binary(op, tv).to_numpy()
+            assert np.array_equal(got, fn(uu, v[None, :]).astype(dtype)), (dtype, op, "u op v")
+            got = tv.binary(op, tu).to_numpy()
+            assert np.array_equal(got, fn(v[None, :], uu).astype(dtype)), (dtype, op, "v op u")
+        if np.dtype(dtype).kind == "f":
+            assert np.array_equal(tu.binary("div", tv).to_numpy(), uu / v[None, :])
+            assert np.array_equal(tv.binary("div", tu).to_numpy(), v[None, :] / uu)
+            assert np.array_equal(tu.binary("lt", tv).to_numpy(), uu < v[None, :])
