@@ -55,14 +55,22 @@ def main():
         return float(v) * mult
 
     traffic = {}
+    try:  # captures of earlier rounds stay unless this round re-captured the kernel
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    prev_source = traffic.pop("source", None)
     names = {f"{RND}_tile_cfg2.ncu-rep": "ew_tile_kernel_cfg2_bytes", f"{RND}_rows_cfg1.ncu-rep": "ew_rows_kernel_cfg1_bytes",
              f"{RND}_redrows_cfg3.ncu-rep": "reduce_rows_kernel_cfg3_bytes", f"{RND}_cols_cfg3.ncu-rep": "reduce_cols_kernel_cfg3_bytes"}
     for rep, key in names.items():
         if rep in full:
             traffic[key] = int(round(gb(full[rep]["dram__bytes_read.sum"]) + gb(full[rep]["dram__bytes_write.sum"])))
-    traffic["source"] = (f"profiles/{RND}_ncu_full_summary.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of one "
-                         "`ncu --set full --clock-control none` capture per kernel; algorithmic bytes: cfg2 8,589,934,592, "
-                         "cfg1 1,073,807,360, cfg3 2,147,614,720 (rows) / 2,147,614,720 (cols)")
+    import datetime
+    fresh = [k for rep, k in names.items() if rep in full]
+    traffic["source"] = (f"profiles/{RND}_ncu_full_summary.json ({datetime.date.today().isoformat()}; re-captured: {', '.join(fresh) or 'none'}): "
+                         "dram__bytes_read.sum + dram__bytes_write.sum per launch of one `ncu --set full --clock-control none` "
+                         "capture per kernel; algorithmic bytes: cfg2 8,589,934,592, cfg1 1,073,807,360, cfg3 2,147,614,720 (rows) / "
+                         "2,147,614,720 (cols)" + (f" | earlier: {prev_source[:60]}..." if prev_source and RND not in prev_source else ""))
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print(json.dumps(traffic, indent=1))
     print("\n".join(out[:12]))
