@@ -29,6 +29,26 @@ void *workspace(rc_device *d, size_t nbytes) {
     return p;
 }
 
+void upload_small(rc_device *d, void *dst_dev, const void *src, size_t nbytes) {
+    if (nbytes == 0) return;
+    if (nbytes > rc_device::STAGE_BYTES) {
+        RC_CUDA(cudaMemcpyAsync(dst_dev, src, nbytes, cudaMemcpyHostToDevice, d->stream));
+        return;
+    }
+    std::lock_guard<std::mutex> lock(d->stage_mu);
+    const int s = d->stage_next;
+    d->stage_next = (s + 1) % rc_device::STAGE_SLOTS;
+    if (!d->stage_buf[s]) {
+        RC_CUDA(cudaHostAlloc(&d->stage_buf[s], rc_device::STAGE_BYTES, cudaHostAllocPortable));
+        RC_CUDA(cudaEventCreateWithFlags(&d->stage_ev[s], cudaEventDisableTiming));
+    } else {
+        RC_CUDA(cudaEventSynchronize(d->stage_ev[s]));  // the copy that last used this slot has left it
+    }
+    std::memcpy(d->stage_buf[s], src, nbytes);
+    RC_CUDA(cudaMemcpyAsync(dst_dev, d->stage_buf[s], nbytes, cudaMemcpyHostToDevice, d->stream));
+    RC_CUDA(cudaEventRecord(d->stage_ev[s], d->stream));
+}
+
 void *scalar_slot(rc_device *d, void **host) {
     if (!d->slot_host) {
         void *h = nullptr, *p = nullptr;
@@ -264,6 +284,10 @@ int rc_device_destroy(rc_device *dev) {
         cudaStreamSynchronize(dev->stream);
         if (dev->ws) cudaFree(dev->ws);
         if (dev->slot_host) cudaFreeHost(dev->slot_host);
+        for (int i = 0; i < rc_device::STAGE_SLOTS; ++i) {
+            if (dev->stage_buf[i]) cudaFreeHost(dev->stage_buf[i]);
+            if (dev->stage_ev[i]) cudaEventDestroy(dev->stage_ev[i]);
+        }
         if (dev->own_stream) cudaStreamDestroy(dev->stream);
         delete dev;
     });

@@ -32,6 +32,14 @@ struct rc_device {
     std::mutex slot_mu;
     void *slot_host = nullptr;
     void *slot_dev = nullptr;
+    // pinned staging ring for small host arguments that must reach the device (index lists of rc_index_select):
+    // cudaMemcpyAsync from PAGEABLE memory synchronises the stream first, which would serialise back-to-back calls.
+    static constexpr int STAGE_SLOTS = 4;
+    static constexpr size_t STAGE_BYTES = 1u << 20;
+    std::mutex stage_mu;
+    void *stage_buf[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    int stage_next = 0;
 };
 
 namespace rc {
@@ -58,6 +66,9 @@ inline void after_launch(rc_device *d, const char *what) {
 }
 
 void *workspace(rc_device *d, size_t nbytes);  // stream-ordered scratch, valid until the next call
+// H2D copy of a small host array without blocking on the stream: through the handle's pinned ring when it fits
+// (<= STAGE_BYTES), else a plain cudaMemcpyAsync.  `src` may be freed as soon as the call returns.
+void upload_small(rc_device *d, void *dst_dev, const void *src, size_t nbytes);
 void *scalar_slot(rc_device *d, void **host);  // device view of the handle's mapped host slot (caller holds slot_mu)
 
 }  // namespace rc

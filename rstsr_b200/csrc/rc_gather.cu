@@ -147,6 +147,43 @@ __global__ void __launch_bounds__(GT_BLOCK) index_select_smem_kernel(const __gri
     for (; t < n_idx; t += GT_BLOCK) dst[(int64_t)t * d.sc_axis] = row[idx[t]];
 }
 
+// The same gather when a row does NOT fit in shared memory but the indices are locally clustered (monotone selections:
+// every other column, a mask, a few columns dropped): the output is cut into windows of `win_w` consecutive indices, the
+// host records the source span [lo, lo + span) each window touches, and a CTA stages just that span (coalesced) before it
+// gathers from shared memory and writes its window (coalesced).  Random indices over a long row keep the direct kernel:
+// every 8-byte read is a 32-byte L2 sector either way, and sorting would cost a second pass.
+template <class U>
+__global__ void __launch_bounds__(GT_BLOCK) index_select_window_kernel(const __grid_constant__ SelDesc d, U *__restrict__ c,
+                                                                       const U *__restrict__ a,
+                                                                       const int64_t *__restrict__ idx,
+                                                                       const int64_t *__restrict__ win, int win_w,
+                                                                       FastDiv div_chunks) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    U *buf = reinterpret_cast<U *>(sel_smem);
+    uint32_t r, chunk;
+    div_chunks.divmod(blockIdx.x, r, chunk);
+    int64_t ro, ri;
+    rest_offsets(d.rest, r, ro, ri);
+    const int64_t lo = win[2 * chunk];
+    const int span = (int)win[2 * chunk + 1];
+    const U *src = a + ri + lo;
+    int t = threadIdx.x;
+    for (; t + (GT_ITEMS - 1) * GT_BLOCK < span; t += GT_ITEMS * GT_BLOCK) {
+        U v[GT_ITEMS];
+#pragma unroll
+        for (int u = 0; u < GT_ITEMS; ++u) v[u] = src[t + u * GT_BLOCK];
+#pragma unroll
+        for (int u = 0; u < GT_ITEMS; ++u) buf[t + u * GT_BLOCK] = v[u];
+    }
+    for (; t < span; t += GT_BLOCK) buf[t] = src[t];
+    __syncthreads();
+    const int64_t i0 = (int64_t)chunk * win_w;
+    const int n = (int)(d.n_idx - i0 < win_w ? d.n_idx - i0 : win_w);
+    U *dst = c + ro + i0 * d.sc_axis;
+    const int64_t *ix = idx + i0;
+    for (t = threadIdx.x; t < n; t += GT_BLOCK) dst[(int64_t)t * d.sc_axis] = buf[ix[t] - lo];
+}
+
 // ---------------- pack_tri ----------------
 struct TriMoveDesc {
     RestDesc rest;       // s_out: strides of the OUTPUT operand, s_in: of the input
@@ -485,6 +522,20 @@ void launch_select_smem(rc_device *dev, const SelDesc &d, void *c, int64_t bc, c
     after_launch(dev, "index_select_smem_kernel");
 }
 
+constexpr int SEL_WIN_W = 2048;                 // outputs per CTA of the windowed gather
+constexpr int64_t SEL_WIN_SPAN_BYTES = 48 * 1024;  // largest source span one window may touch
+
+template <class U>
+void launch_select_window(rc_device *dev, const SelDesc &d, void *c, int64_t bc, const void *a, int64_t ba, const int64_t *idx,
+                          const int64_t *win, int64_t n_chunks, int64_t max_span) {
+    const size_t smem = (size_t)max_span * sizeof(U);
+    if (smem > 48 * 1024)
+        RC_CUDA(cudaFuncSetAttribute(index_select_window_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    index_select_window_kernel<U><<<(unsigned)(d.rest.n_rest * n_chunks), GT_BLOCK, smem, dev->stream>>>(
+        d, static_cast<U *>(c) + bc, static_cast<const U *>(a) + ba, idx, win, SEL_WIN_W, FastDiv((uint32_t)n_chunks));
+    after_launch(dev, "index_select_window_kernel");
+}
+
 template <class U>
 void launch_pack(rc_device *dev, const TriMoveDesc &d, void *p, int64_t bp, const void *f, int64_t bf) {
     pack_tri_kernel<U><<<grid_for(d.total), GT_BLOCK, 0, dev->stream>>>(d, static_cast<U *>(p) + bp,
@@ -601,17 +652,51 @@ int rc_index_select(rc_device *dev, rc_dtype t, void *c, const rc_layout *lc_, c
         if (d.total >= (1ll << 31)) d.rest.big = 1;
         else d.split = FastDiv((uint32_t)(d.idx_fastest ? d.n_idx : d.rest.n_rest));
 
+        // staged-row path: gather along the input's contiguous axis, most of each row wanted, rows fit in smem
+        const bool staged = d.idx_fastest && d.sa_axis == 1 && d.n_src * e <= SEL_SMEM_MAX && 2 * n_indices >= d.n_src &&
+                            d.n_src >= 256 && d.rest.n_rest >= dev->sm_count && d.rest.n_rest < (1ll << 31) &&
+                            n_indices < (1ll << 31);
+        // windowed path: the same gather on longer rows when every window of SEL_WIN_W indices touches a short source span
+        std::vector<int64_t> win;
+        int64_t n_chunks = 0, max_span = 0;
+        static const bool window_on = [] { const char *v = getenv("RC_SEL_WINDOW"); return !(v && v[0] == '0'); }();
+        if (window_on && !staged && d.idx_fastest && d.sa_axis == 1 && n_indices >= 4 * SEL_WIN_W && n_indices < (1ll << 31) && e <= 8) {
+            n_chunks = (n_indices + SEL_WIN_W - 1) / SEL_WIN_W;
+            win.resize((size_t)n_chunks * 2);
+            int64_t total_span = 0;
+            bool ok = d.rest.n_rest * n_chunks < (1ll << 31);
+            for (int64_t k = 0; k < n_chunks && ok; ++k) {
+                const int64_t i0 = k * SEL_WIN_W, i1 = std::min<int64_t>(n_indices, i0 + SEL_WIN_W);
+                int64_t lo = indices[i0], hi = indices[i0];
+                for (int64_t i = i0 + 1; i < i1; ++i) { lo = std::min(lo, indices[i]); hi = std::max(hi, indices[i]); }
+                const int64_t span = hi - lo + 1;
+                ok = span * e <= SEL_WIN_SPAN_BYTES;
+                win[2 * k] = lo;
+                win[2 * k + 1] = span;
+                total_span += span;
+                max_span = std::max(max_span, span);
+            }
+            // Dense clustered selections only (at least ~5 of 8 source elements wanted): measured on (2048, 32768) f64, a 70 %
+            // mask gains (3.2 -> 3.8 TB/s) while "every other column" loses (3.2 -> 2.9): with half of every sector wanted
+            // the direct kernel's sector reads already share sectors between neighbours and move no more than the window.
+            if (!ok || 5 * total_span > 8 * n_indices) n_chunks = 0;
+        }
+
         int64_t *idx_dev = nullptr;
-        cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&idx_dev), (size_t)n_indices * 8, dev->stream);
+        cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&idx_dev), (size_t)(n_indices + 2 * n_chunks) * 8, dev->stream);
         if (err != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(err));
         try {
-            RC_CUDA(cudaMemcpyAsync(idx_dev, indices, (size_t)n_indices * 8, cudaMemcpyHostToDevice, dev->stream));
-            // staged-row path: gather along the input's contiguous axis, most of each row wanted, rows fit in smem
-            const bool staged = d.idx_fastest && d.sa_axis == 1 && d.n_src * e <= SEL_SMEM_MAX && 2 * n_indices >= d.n_src &&
-                                d.n_src >= 256 && d.rest.n_rest >= dev->sm_count && d.rest.n_rest < (1ll << 31) &&
-                                n_indices < (1ll << 31);
+            upload_small(dev, idx_dev, indices, (size_t)n_indices * 8);  // pinned ring: no stream sync between calls
+            if (n_chunks > 0) {
+                upload_small(dev, idx_dev + n_indices, win.data(), (size_t)n_chunks * 16);
+                w = -100 - e;
+            }
             if (staged) w = -e;
             switch (w) {
+                case -101: launch_select_window<uint8_t>(dev, d, c, bc, a, ba, idx_dev, idx_dev + n_indices, n_chunks, max_span); break;
+                case -102: launch_select_window<uint16_t>(dev, d, c, bc, a, ba, idx_dev, idx_dev + n_indices, n_chunks, max_span); break;
+                case -104: launch_select_window<uint32_t>(dev, d, c, bc, a, ba, idx_dev, idx_dev + n_indices, n_chunks, max_span); break;
+                case -108: launch_select_window<uint64_t>(dev, d, c, bc, a, ba, idx_dev, idx_dev + n_indices, n_chunks, max_span); break;
                 case -1: launch_select_smem<uint8_t>(dev, d, c, bc, a, ba, idx_dev); break;
                 case -2: launch_select_smem<uint16_t>(dev, d, c, bc, a, ba, idx_dev); break;
                 case -4: launch_select_smem<uint32_t>(dev, d, c, bc, a, ba, idx_dev); break;

@@ -48,6 +48,26 @@ rep("index_select cols (8192,8192) f64, 8192 random cols", 2 * N * 8, lambda: de
 rep("torch.index_select rows", 2 * N * 8, lambda: torch.index_select(A, 0, tidx))
 rep("torch.index_select cols", 2 * N * 8, lambda: torch.index_select(A, 1, tidx))
 
+# long rows (256 KiB each): clustered selections take the windowed kernel, scattered ones the direct kernel
+m_rows, n_src = 2048, 32768
+Nl = m_rows * n_src
+al = torch.rand(Nl, dtype=torch.float64, device="cuda")
+Al = al.view(m_rows, n_src)
+ra_l = dev.wrap(al.data_ptr(), Nl, np.float64)
+for name, ix in (("every other column", np.arange(0, n_src, 2)), ("random 70 % mask", np.nonzero(rng.random(n_src) < 0.7)[0]),
+                 ("scattered random", rng.integers(0, n_src, n_src // 2))):
+    ix = ix.astype(np.int64)
+    cl = torch.empty(m_rows * ix.size, dtype=torch.float64, device="cuda")
+    rc_l = dev.wrap(cl.data_ptr(), cl.numel(), np.float64)
+    lsrc, ldst = Layout((m_rows, n_src), (n_src, 1)), Layout((m_rows, ix.size), (ix.size, 1))
+    tix = torch.from_numpy(ix).cuda()
+    dev.index_select(rc_l, ldst, ra_l, lsrc, 1, ix)
+    assert torch.equal(cl.view(m_rows, ix.size), torch.index_select(Al, 1, tix))
+    rep(f"index_select cols of (2048,32768) f64: {name} (output bytes x 2)", 2 * cl.numel() * 8, lambda: dev.index_select(rc_l, ldst, ra_l, lsrc, 1, ix))
+    rep("   torch.index_select (indices on the device)", 2 * cl.numel() * 8, lambda: torch.index_select(Al, 1, tix))
+    del cl
+del al
+
 for batch, m in ((64, 1024), (4, 4096)):
     tp = m * (m + 1) // 2
     nf, npk = batch * m * m, batch * tp

@@ -105,6 +105,33 @@ def test_index_select_large_rows(dev):
     assert np.array_equal(f[1:, 1:].index_select(0, idx[:500] % 4095).to_numpy(), a.astype(np.float32)[1:, 1:][idx[:500] % 4095])
 
 
+def test_index_select_long_rows_clustered_indices(dev):
+    """gather along the contiguous axis of rows too long for shared memory: monotone / clustered selections take the
+    windowed kernel (source span of every 2048-index window staged in smem), scattered ones the direct kernel"""
+    rng = np.random.default_rng(seed_of("selwin"))
+    n_src = 40000
+    a = rng.standard_normal((37, n_src))
+    t = rt.asarray(a, dev)
+    every_other = np.arange(0, n_src, 2)
+    dropped = np.delete(np.arange(n_src), rng.integers(0, n_src, 500))
+    mask = np.nonzero(rng.random(n_src) < 0.7)[0]
+    locally_shuffled = np.arange(20000).reshape(-1, 50)[:, ::-1].reshape(-1)      # clustered but not monotone
+    repeated = np.repeat(np.arange(0, 12000, 3), 3)
+    scattered = rng.integers(0, n_src, 30000)                                      # falls back to the direct kernel
+    for idx in (every_other, dropped, mask, locally_shuffled, repeated, scattered):
+        assert np.array_equal(t.index_select(1, idx).to_numpy(), a[:, idx])
+    for dt in (np.float32, np.int16, np.uint8):
+        b = (a * 50).astype(dt)
+        assert np.array_equal(rt.asarray(b, dev).index_select(-1, mask).to_numpy(), b[:, mask])
+    # sliced source rows (offset, pitch) and a strided output
+    assert np.array_equal(t[3:, 11:].index_select(1, every_other[:15000]).to_numpy(), a[3:, 11:][:, every_other[:15000]])
+    out = rt.full([37, 2 * mask.size], -1.0, dev)
+    oc = out[:, ::2]
+    dev.index_select(oc.raw, oc.layout, t.raw, t.layout, 1, mask)
+    o = out.to_numpy()
+    assert np.array_equal(o[:, ::2], a[:, mask]) and np.all(o[:, 1::2] == -1.0)
+
+
 # ---------------- pack_tri / unpack_tri ----------------
 def test_reference_kats(dev, dev_col):
     a = np.arange(48.0)
