@@ -13,6 +13,10 @@ pub const RC_U32: c_int = 7;
 pub const RC_U64: c_int = 8;
 pub const RC_F32: c_int = 9;
 pub const RC_F64: c_int = 10;
+pub const RC_F16: c_int = 11;
+pub const RC_BF16: c_int = 12;
+pub const RC_C32: c_int = 13;
+pub const RC_C64: c_int = 14;
 
 // rc_order / rc_iter_order
 pub const RC_ROW_MAJOR: c_int = 0;

@@ -254,3 +254,6 @@ where
 
 impl<D> DeviceComplexFloatAPI<f32, D> for DeviceCuda where D: DimAPI {}
 impl<D> DeviceComplexFloatAPI<f64, D> for DeviceCuda where D: DimAPI {}
+// Complex<f32> / Complex<f64>: the library covers storage, copies, casts, + - * /, neg, conj / abs / real / imag / square,
+// the listed math functions and sum / prod / mean (include/rstsr_cuda.h, RC_C32 / RC_C64); the umbrella bound asks for the
+// full unary set (asin .. atanh, floor-like ops are real-only), so it is NOT claimed for complex types yet.

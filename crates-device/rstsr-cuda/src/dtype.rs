@@ -23,6 +23,11 @@ impl_dtype!(
 #[cfg(target_pointer_width = "64")]
 impl_dtype!(isize => RC_I64, usize => RC_U64);
 
+// half and complex element types (round 2): same bit layout as half::{f16, bf16} and num::Complex<f32 | f64>
+impl_dtype!(num::complex::Complex<f32> => RC_C32, num::complex::Complex<f64> => RC_C64);
+#[cfg(feature = "half")]
+impl_dtype!(half::f16 => RC_F16, half::bf16 => RC_BF16);
+
 /// `MaybeUninit<T>` storage is the same bytes as `T` storage (uninit_impl / assume_init_impl).
 unsafe impl<T: CudaDType> CudaDType for MaybeUninit<T> {
     const CODE: c_int = T::CODE;

@@ -60,7 +60,18 @@ typedef enum rc_dtype {
     RC_U32 = 7,
     RC_U64 = 8, /* also usize */
     RC_F32 = 9,
-    RC_F64 = 10
+    RC_F64 = 10,
+    /* round 2: half and complex element types (half::f16, half::bf16, num::Complex<f32>, num::Complex<f64>).
+     * Arithmetic on the half types is f32 compute + ONE rounding, as the `half` crate does; complex mul / div use the
+     * textbook formulas of num-complex.  Covered: storage, copy / to_contig / gather (raw words), fill, casts
+     * half <-> f32 / f64 / bool and real -> complex, c32 <-> c64; + - * / neg, comparisons (== != only for complex),
+     * maximum / minimum and the float math functions for half; abs / real / imag (real output), conj, square, exp, log,
+     * sqrt, sin, cos, sinh, cosh, tanh, reciprocal for complex; sum / prod / mean (all four), max / min (half).
+     * Anything else on these types is RC_ERR_UNIMPLEMENTED. */
+    RC_F16 = 11,
+    RC_BF16 = 12,
+    RC_C32 = 13, /* 8 bytes: re, im as f32 */
+    RC_C64 = 14  /* 16 bytes: re, im as f64 */
 } rc_dtype;
 
 /* FlagOrder (rstsr-common/src/flags.rs:60-87) */

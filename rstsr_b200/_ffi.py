@@ -19,7 +19,7 @@ STATUS_NAMES = {0: "Ok", 1: "ValueOutOfRange", 2: "InvalidValue", 3: "InvalidLay
                 5: "DeviceMismatch", 6: "UnImplemented", 7: "MemoryError", 8: "DeviceError", 9: "IndexError"}
 
 # dtype codes
-BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64 = range(11)
+BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, F16, BF16, C32, C64 = range(15)
 ROW_MAJOR, COL_MAJOR = 0, 1
 ITER_C, ITER_F, ITER_A, ITER_K = range(4)
 

@@ -90,6 +90,7 @@ rc_dtype redop_out_dtype(rc_redop op, rc_dtype t) {
 
 void run_reduce(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out,
                 int64_t mean_count) {
+    if (dtype_is_extended(t)) { run_reduce_extx(dev, op, t, cr, a, out, mean_count); return; }
     switch (t) {  // narrow integers: base and "next" ops live in one TU per width
         case RC_I8: run_reduce_i8(dev, op, cr, a, out, mean_count); return;
         case RC_U8: run_reduce_u8(dev, op, cr, a, out, mean_count); return;
@@ -160,7 +161,22 @@ void host_cast_to(rc_dtype tc, TIn v, bool in_bool, void *out8) {
     raise(RC_ERR_INVALID_VALUE, "unknown dtype");
 }
 
-void host_scalar_cast(rc_dtype tc, rc_dtype tf, const void *src, void *out8) {
+void host_scalar_cast_prim(rc_dtype tc, rc_dtype tf, const void *src, void *out8);
+
+// out16: 16 bytes (c64 is the widest element)
+void host_scalar_cast(rc_dtype tc, rc_dtype tf, const void *src, void *out16) {
+    std::memset(out16, 0, 16);
+    if (!dtype_is_extended(tc) && !dtype_is_extended(tf)) { host_scalar_cast_prim(tc, tf, src, out16); return; }
+    if (tc == tf) { std::memcpy(out16, src, dtype_size(tc)); return; }
+    double re = 0.0, im = 0.0;
+    if (dtype_is_extended(tf)) host_from_ext(tf, src, &re, &im);
+    else { unsigned char d8[8]; host_scalar_cast_prim(RC_F64, tf, src, d8); std::memcpy(&re, d8, 8); }
+    if (dtype_is_extended(tc)) { host_to_ext(tc, re, im, out16); return; }
+    RC_CHECK(!dtype_is_complex(tf), RC_ERR_UNIMPLEMENTED, "complex scalars do not cast to real types");
+    host_scalar_cast_prim(tc, RC_F64, &re, out16);
+}
+
+void host_scalar_cast_prim(rc_dtype tc, rc_dtype tf, const void *src, void *out8) {
 #define RC_HS(DT, CT, INB) case DT: { CT v; std::memcpy(&v, src, sizeof(CT)); host_cast_to<CT>(tc, v, INB, out8); return; }
     switch (tf) {
         RC_HS(RC_BOOL, uint8_t, true)
@@ -179,6 +195,10 @@ bool is_predicate(rc_unop op) { return op >= RC_ISNAN && op <= RC_SIGNBIT; }
 
 void dispatch_binary(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args) {
     if (c.empty) return;
+    if (dtype_is_extended(t)) {
+        if (run_binary_ext(dev, op, t, c, args)) return;
+        raise(RC_ERR_UNIMPLEMENTED, std::string("this binary op is not implemented for dtype ") + dtype_name(t));
+    }
     if (is_cmp(op)) run_binary_cmp(dev, op, t, c, args);
     else if (is_bit(op)) run_binary_bit(dev, op, t, c, args);
     else if (is_func(op)) run_binary_func(dev, op, t, c, args);
@@ -196,8 +216,10 @@ void reduce_into_nolock(rc_device *dev, rc_redop op, rc_dtype t, const void *a, 
     if (op == RC_MAX || op == RC_MIN)
         RC_CHECK(la.size() != 0, RC_ERR_INVALID_VALUE,
                  op == RC_MAX ? "zero-size array is not supported for max" : "zero-size array is not supported for min");
-    if (op == RC_MEAN || op == RC_VAR || op == RC_STD || op == RC_L2_NORM)
-        RC_CHECK(dtype_is_float(t), RC_ERR_UNIMPLEMENTED, "mean / var / std / l2_norm require a floating-point dtype");
+    if (op == RC_MEAN)
+        RC_CHECK(dtype_is_float(t) || dtype_is_extended(t), RC_ERR_UNIMPLEMENTED, "mean requires a floating-point dtype");
+    if (op == RC_VAR || op == RC_STD || op == RC_L2_NORM)
+        RC_CHECK(dtype_is_float(t), RC_ERR_UNIMPLEMENTED, "var / std / l2_norm require f32 or f64");
     if (op == RC_ALL || op == RC_ANY) RC_CHECK(t == RC_BOOL, RC_ERR_UNIMPLEMENTED, "all / any take a bool tensor");
     const bool arg = (op == RC_ARGMIN || op == RC_ARGMAX);
     if (arg)  // reduce_all_unraveled_arg_cpu_serial: "empty sequence is not allowed for reduce_arg."
@@ -619,7 +641,7 @@ int rc_fill(rc_device *dev, rc_dtype tc, void *c, const rc_layout *lc_, rc_dtype
         CanonEw cn = canon_elementwise({&lc}, true);  // iteration order G (cpu_rayon/assignment.rs:199)
         if (cn.empty) return;
         check_ptr(c, "c");
-        unsigned char v[8];
+        unsigned char v[16];
         host_scalar_cast(tc, tf, fill, v);
         run_fill(dev, tc, cn, c, v);
     });
@@ -717,6 +739,11 @@ int rc_unary_muta_refb(rc_device *dev, rc_unop op, rc_dtype t, void *a, const rc
         check_ptr(a, "a"); check_ptr(b, "b");
         EwArgs args;
         args.c = a; args.a = b;
+        if (dtype_is_extended(t)) {
+            RC_CHECK(run_unary_ext(dev, op, t, cn, args), RC_ERR_UNIMPLEMENTED,
+                     std::string("this unary op is not implemented for dtype ") + dtype_name(t));
+            return;
+        }
         run_unary(dev, op, t, cn, args);
     });
 }
@@ -735,6 +762,13 @@ int rc_unary_muta(rc_device *dev, rc_unop op, rc_dtype t, void *a, const rc_layo
         cn.base[1] = one.base[0];
         EwArgs args;
         args.c = a; args.a = a;
+        if (dtype_is_extended(t)) {
+            RC_CHECK(!(dtype_is_complex(t) && (op == RC_ABS || op == RC_REAL || op == RC_IMAG)), RC_ERR_INVALID_VALUE,
+                     "abs / real / imag of a complex tensor change the element type: no in-place form");
+            RC_CHECK(run_unary_ext(dev, op, t, cn, args), RC_ERR_UNIMPLEMENTED,
+                     std::string("this unary op is not implemented for dtype ") + dtype_name(t));
+            return;
+        }
         run_unary(dev, op, t, cn, args);
     });
 }
@@ -743,7 +777,12 @@ int rc_binop_out_dtype(rc_binop op, rc_dtype t, rc_dtype *out) {
     return guard([&] { RC_CHECK(out, RC_ERR_INVALID_VALUE, "null out"); *out = is_cmp(op) ? RC_BOOL : t; });
 }
 int rc_unop_out_dtype(rc_unop op, rc_dtype t, rc_dtype *out) {
-    return guard([&] { RC_CHECK(out, RC_ERR_INVALID_VALUE, "null out"); *out = is_predicate(op) ? RC_BOOL : t; });
+    return guard([&] {
+        RC_CHECK(out, RC_ERR_INVALID_VALUE, "null out");
+        *out = is_predicate(op) ? RC_BOOL : t;
+        // ExtNum::AbsOut of a complex number is its real type (abs / real / imag; auto_impl/op_binary_common.rs:122-204)
+        if (dtype_is_complex(t) && (op == RC_ABS || op == RC_REAL || op == RC_IMAG)) *out = (t == RC_C32) ? RC_F32 : RC_F64;
+    });
 }
 int rc_redop_out_dtype(rc_redop op, rc_dtype t, rc_dtype *out) {
     return guard([&] { RC_CHECK(out, RC_ERR_INVALID_VALUE, "null out"); *out = redop_out_dtype(op, t); });

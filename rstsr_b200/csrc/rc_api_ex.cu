@@ -38,6 +38,8 @@ rc_dtype unsigned_of_bits(int bits) { return bits <= 8 ? RC_U8 : bits <= 16 ? RC
 
 rc_dtype promote(rc_dtype a, rc_dtype b) {
     if (a == b) return a;
+    RC_CHECK(!dtype_is_extended(a) && !dtype_is_extended(b), RC_ERR_UNIMPLEMENTED,
+             "promotion between half / complex and other element types is not implemented");
     if (a == RC_BOOL) return b;  // bool x T -> T (promotion.rs:123-181)
     if (b == RC_BOOL) return a;
     const bool fa = dtype_is_float(a), fb = dtype_is_float(b);
@@ -71,6 +73,7 @@ bool is_float_func(rc_binop op) {
 
 enum PowKind { POW_SAME = 0, POW_FLOAT_INT = 1, POW_INT_UINT = 2 };
 PowKind pow_kind(rc_dtype ta, rc_dtype tb) {
+    if (dtype_is_half(ta) && tb == ta) return POW_SAME;  // num_traits::Float::powf of the half types (through f32)
     if (dtype_is_float(ta)) {
         if (tb == ta) return POW_SAME;
         if (tb == RC_I8 || tb == RC_U8 || tb == RC_I16 || tb == RC_U16 || tb == RC_I32) return POW_FLOAT_INT;
@@ -83,6 +86,15 @@ PowKind pow_kind(rc_dtype ta, rc_dtype tb) {
 
 // compute type K (both operands are brought to it) and output type of `op` for operand types (ta, tb)
 void op_types(rc_binop op, rc_dtype ta, rc_dtype tb, rc_dtype *k, rc_dtype *out) {
+    if (dtype_is_extended(ta) || dtype_is_extended(tb)) {
+        // half / complex operands: same type on both sides (cast first otherwise); the library's promotion table covers the
+        // Rust primitives, as impl_promotion_asable! does
+        RC_CHECK(ta == tb, RC_ERR_UNIMPLEMENTED,
+                 std::string("mixed operand types with ") + dtype_name(dtype_is_extended(ta) ? ta : tb) + ": cast one operand first");
+        *k = ta;
+        *out = is_cmp_op(op) ? RC_BOOL : ta;
+        return;
+    }
     if (op == RC_POW) {
         pow_kind(ta, tb);
         *k = ta;
@@ -262,7 +274,7 @@ int rc_op_mutc_refa_numb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, c
         RC_CHECK(b_host != nullptr, RC_ERR_INVALID_VALUE, "null pointer: b");
         rc_dtype k;
         check_out_type(op, tc, ta, tb, &k);
-        unsigned char sb[8];
+        unsigned char sb[16];
         if (op == RC_POW && pow_kind(ta, tb) != POW_SAME) {
             cast_host_scalar(pow_kind(ta, tb) == POW_FLOAT_INT ? RC_I32 : RC_U32, tb, b_host, sb);
             Layout lcc = from_c(lc), la = from_c(la_);
@@ -290,7 +302,7 @@ int rc_op_mutc_numa_refb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, c
         RC_CHECK(a_host != nullptr, RC_ERR_INVALID_VALUE, "null pointer: a");
         rc_dtype k;
         check_out_type(op, tc, ta, tb, &k);
-        unsigned char sa[8];
+        unsigned char sa[16];
         if (op == RC_POW && pow_kind(ta, tb) != POW_SAME) {
             const rc_dtype te = pow_kind(ta, tb) == POW_FLOAT_INT ? RC_I32 : RC_U32;
             Layout lcc = from_c(lc), lb = from_c(lb_);

@@ -71,11 +71,16 @@ inline size_t dtype_size(rc_dtype t) {
         case RC_BOOL: case RC_I8: case RC_U8: return 1;
         case RC_I16: case RC_U16: return 2;
         case RC_I32: case RC_U32: case RC_F32: return 4;
-        case RC_I64: case RC_U64: case RC_F64: return 8;
+        case RC_I64: case RC_U64: case RC_F64: case RC_C32: return 8;
+        case RC_F16: case RC_BF16: return 2;
+        case RC_C64: return 16;
     }
     raise(RC_ERR_INVALID_VALUE, "unknown dtype");
 }
 inline bool dtype_is_float(rc_dtype t) { return t == RC_F32 || t == RC_F64; }
+inline bool dtype_is_half(rc_dtype t) { return t == RC_F16 || t == RC_BF16; }
+inline bool dtype_is_complex(rc_dtype t) { return t == RC_C32 || t == RC_C64; }
+inline bool dtype_is_extended(rc_dtype t) { return dtype_is_half(t) || dtype_is_complex(t); }
 inline bool dtype_is_signed_int(rc_dtype t) { return t == RC_I8 || t == RC_I16 || t == RC_I32 || t == RC_I64; }
 inline bool dtype_is_unsigned_int(rc_dtype t) { return t == RC_U8 || t == RC_U16 || t == RC_U32 || t == RC_U64; }
 inline bool dtype_is_int(rc_dtype t) { return dtype_is_signed_int(t) || dtype_is_unsigned_int(t); }

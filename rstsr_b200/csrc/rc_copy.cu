@@ -48,6 +48,8 @@ struct ArbDesc {
     int64_t stride_c[RC_MAX_NDIM], stride_a[RC_MAX_NDIM];
 };
 
+struct alignas(16) ArbWord16 { uint64_t lo, hi; };
+
 template <class F>
 __global__ void __launch_bounds__(256) arb_kernel(const __grid_constant__ ArbDesc d, typename F::TO *c, const typename F::TA *a) {
     uint32_t idx = blockIdx.x * 256u + threadIdx.x;
@@ -87,7 +89,12 @@ void run_cast(rc_device *dev, rc_dtype tc, rc_dtype ta, const CanonEw &c, const 
             case 2: ew_launch<FIdentity<uint16_t>>(dev, c, args); return;
             case 4: ew_launch<FIdentity<uint32_t>>(dev, c, args); return;
             case 8: ew_launch<FIdentity<uint64_t>>(dev, c, args); return;
+            case 16: run_copy16(dev, c, args); return;
         }
+    }
+    if (dtype_is_extended(tc) || dtype_is_extended(ta)) {
+        if (run_cast_ext(dev, tc, ta, c, args)) return;
+        raise(RC_ERR_UNIMPLEMENTED, std::string("cast ") + dtype_name(ta) + " -> " + dtype_name(tc) + " is not implemented");
     }
     switch (tc) {
         case RC_BOOL: cast_from<uint8_t>(dev, ta, c, args, true); return;
@@ -114,6 +121,7 @@ void run_fill(rc_device *dev, rc_dtype tc, const CanonEw &c, void *c_ptr, const 
         case 2: ew_launch<FFill<uint16_t>, false>(dev, c, args); return;
         case 4: ew_launch<FFill<uint32_t>, false>(dev, c, args); return;
         case 8: ew_launch<FFill<uint64_t>, false>(dev, c, args); return;
+        case 16: run_fill16(dev, c, args); return;
     }
     unsupported("fill", tc);
 }
@@ -146,6 +154,7 @@ void run_assign_arbitrary_generic(rc_device *dev, rc_dtype tc, void *c, const La
         case 2: arb_launch<FIdentity<uint16_t>>(dev, d, pc, pa); return;
         case 4: arb_launch<FIdentity<uint32_t>>(dev, d, pc, pa); return;
         case 8: arb_launch<FIdentity<uint64_t>>(dev, d, pc, pa); return;
+        case 16: arb_launch<FIdentity<ArbWord16>>(dev, d, pc, pa); return;
     }
     unsupported("copy", tc);
 }

@@ -446,7 +446,9 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
                 } else {
                     out = F::apply(va);
                 }
-                __stcs(pc + (int64_t)u * d.sy[0] + v, out);
+                Pack<TO, 1> po;
+                po.v[0] = out;
+                st_stream<TO, 1>(pc + (int64_t)u * d.sy[0] + v, po);
             }
         }
     }
@@ -681,7 +683,11 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_rect_kernel(const __g
         } else {
             out = F::apply(va);
         }
-        if (ok) __stcs(pc + ((int32_t)yd * syc + (int32_t)xd), out);
+        if (ok) {
+            Pack<TO, 1> po;
+            po.v[0] = out;
+            st_stream<TO, 1>(pc + ((int32_t)yd * syc + (int32_t)xd), po);
+        }
     }
 }
 
@@ -839,6 +845,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                 if (slot_b >= 0) tm_b = (c.stride[slot_b][ydim] == 1 && c.stride[slot_b][0] > 1 && yb == ydim) ? TILE_STAGED : TILE_DIRECT;
                 // one short and one long extent: rectangular tile, the short extent taken whole
                 const size_t esz_staged = (ya == ydim && slot_a >= 0) ? sizeof(TA) : sizeof(TB);
+                if constexpr (sizeof(TA) <= 8 && sizeof(TB) <= 8 && sizeof(TO) <= 8)  // 16-byte elements (c64): square tile only
                 if (rect_short_y(t.nx, t.ny, esz_staged) || rect_short_x(t.nx, t.ny, sizeof(TO))) {
                     TileRectDesc r;
                     std::memset(&r, 0, sizeof(r));

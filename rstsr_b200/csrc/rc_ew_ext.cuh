@@ -1,0 +1,74 @@
+// rc_ew_ext.cuh -- functors of the extended element types (f16, bf16, c32, c64; rc_types.cuh), shared by the
+// rc_ew_ext_*.cu translation units (split so that they build in parallel).
+//   half     FViaF32<T, F>: both operands to f32, the f32 functor, ONE rounding back -- `half` crate semantics, and exactly
+//            what NumPy's float16 / ml_dtypes' bfloat16 do, so + - * / are bit-exact against them;
+//   complex  + - * / neg from the operators of rc_types.cuh (num-complex formulas); abs = hypot(re, im) (`norm()`),
+//            real / imag with REAL output, conj, square = z * z, reciprocal = (re / n, -im / n) (`inv()`); the
+//            transcendental functions through thrust::complex (tolerance-compared, like every libm function here).
+#pragma once
+#include <thrust/complex.h>
+
+#include "rc_dispatch.cuh"
+#include "rc_types.cuh"
+
+namespace rc {
+namespace {
+
+// ---------------- half: everything through f32 ----------------
+template <class T, template <class> class FF>
+struct FViaF32 { using TA = T; using TB = T; using TO = T; static constexpr int NIN = FF<float>::NIN;
+    RC_FN T apply(T a) { return T(FF<float>::apply(a.f())); }
+    RC_FN T apply(T a, T b) { return T(FF<float>::apply(a.f(), b.f())); } };
+template <class T, template <class> class FF>
+struct FViaF32Bool { using TA = T; using TB = T; using TO = uint8_t; static constexpr int NIN = FF<float>::NIN;
+    RC_FN uint8_t apply(T a) { return FF<float>::apply(a.f()); }
+    RC_FN uint8_t apply(T a, T b) { return FF<float>::apply(a.f(), b.f()); } };
+
+// ---------------- complex ----------------
+template <class R> struct FCAbs { using TA = cplx<R>; using TB = TA; using TO = R; static constexpr int NIN = 1;
+    RC_FN R apply(TA a) { if constexpr (sizeof(R) == 4) return hypotf(a.re, a.im); else return hypot(a.re, a.im); } };
+template <class R> struct FCReal { using TA = cplx<R>; using TB = TA; using TO = R; static constexpr int NIN = 1; RC_FN R apply(TA a) { return a.re; } };
+template <class R> struct FCImag { using TA = cplx<R>; using TB = TA; using TO = R; static constexpr int NIN = 1; RC_FN R apply(TA a) { return a.im; } };
+template <class R> struct FCConj { using TA = cplx<R>; using TB = TA; using TO = TA; static constexpr int NIN = 1; RC_FN TA apply(TA a) { return TA(a.re, -a.im); } };
+template <class R> struct FCRecip { using TA = cplx<R>; using TB = TA; using TO = TA; static constexpr int NIN = 1;
+    RC_FN TA apply(TA a) { const R n = a.re * a.re + a.im * a.im; return TA(a.re / n, -a.im / n); } };
+#define RC_CPLX_MATH(NAME, EXPR)                                                                             \
+    template <class R> struct NAME { using TA = cplx<R>; using TB = TA; using TO = TA; static constexpr int NIN = 1; \
+        RC_FN TA apply(TA a) { const thrust::complex<R> z(a.re, a.im); const thrust::complex<R> r = EXPR; return TA(r.real(), r.imag()); } };
+RC_CPLX_MATH(FCExp, thrust::exp(z))
+RC_CPLX_MATH(FCLog, thrust::log(z))
+RC_CPLX_MATH(FCSqrt, thrust::sqrt(z))
+RC_CPLX_MATH(FCSin, thrust::sin(z))
+RC_CPLX_MATH(FCCos, thrust::cos(z))
+RC_CPLX_MATH(FCSinh, thrust::sinh(z))
+RC_CPLX_MATH(FCCosh, thrust::cosh(z))
+RC_CPLX_MATH(FCTanh, thrust::tanh(z))
+
+// ---------------- casts ----------------
+template <class TOut, class TIn> struct conv_t {
+    RC_FN TOut go(TIn a) {
+        if constexpr (is_half_t<TIn>::value) {                       // half -> f32 / f64 / bool / other half
+            if constexpr (std::is_same<TOut, uint8_t>::value) return a.f() != 0.0f ? 1 : 0;
+            else if constexpr (is_half_t<TOut>::value) return TOut(a.f());
+            else return (TOut)a.f();
+        } else if constexpr (is_half_t<TOut>::value) {               // f32 / f64 / bool -> half: one rounding
+            return TOut(a);
+        } else if constexpr (is_cplx_t<TIn>::value) {                // c32 <-> c64: componentwise `as`
+            using RO = typename real_of<TOut>::type;
+            return TOut((RO)a.re, (RO)a.im);
+        } else {                                                     // real -> complex: (a as R, 0)
+            using RO = typename real_of<TOut>::type;
+            return TOut((RO)a, (RO)0);
+        }
+    }
+};
+template <class TOut, class TIn> struct FCastX { using TA = TIn; using TB = TIn; using TO = TOut; static constexpr int NIN = 1;
+    RC_FN TOut apply(TIn a) { return conv_t<TOut, TIn>::go(a); } };
+struct BoolIn { uint8_t v; };  // bool source: 0 / 1
+template <class TOut> struct FCastFromBool { using TA = uint8_t; using TB = uint8_t; using TO = TOut; static constexpr int NIN = 1;
+    RC_FN TOut apply(uint8_t a) { return TOut(a ? 1.0f : 0.0f); } };
+
+struct alignas(16) U128 { uint64_t lo, hi; };
+
+}  // namespace
+}  // namespace rc

@@ -28,6 +28,10 @@ const char *dtype_name(rc_dtype t) {
         case RC_U64: return "u64";
         case RC_F32: return "f32";
         case RC_F64: return "f64";
+        case RC_F16: return "f16";
+        case RC_BF16: return "bf16";
+        case RC_C32: return "c32";
+        case RC_C64: return "c64";
     }
     return "?";
 }

@@ -17,6 +17,16 @@ void run_binary_pow_mixed(rc_device *dev, rc_dtype t, const CanonEw &c, const Ew
 void run_isclose(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args);
 // Rust `as` between host scalars (rc_api.cu): 8 bytes out
 void cast_host_scalar(rc_dtype tc, rc_dtype tf, const void *src, void *out8);
+// extended element types f16 / bf16 / c32 / c64 (rc_ew_ext.cu, rc_reduce_extx.cu); the bool functions return false
+// when the op / cast does not exist for the type
+bool run_binary_ext(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+bool run_unary_ext(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+bool run_cast_ext(rc_device *dev, rc_dtype tc, rc_dtype ta, const CanonEw &c, const EwArgs &args);
+void run_copy16(rc_device *dev, const CanonEw &c, const EwArgs &args);
+void run_fill16(rc_device *dev, const CanonEw &c, const EwArgs &args);
+void host_to_ext(rc_dtype tc, double re, double im, void *out16);
+void host_from_ext(rc_dtype t, const void *src, double *re, double *im);
+void run_reduce_extx(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out, int64_t n);
 // a = f(b)
 void run_unary(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
 // c = cast(a) (rc_copy.cu); same dtype moves raw bits

@@ -30,6 +30,7 @@ struct h16 {
     RC_HD explicit h16(float f) { __half h = __float2half_rn(f); bits = *reinterpret_cast<uint16_t *>(&h); }
     RC_HD explicit h16(double d) { __half h = __double2half(d); bits = *reinterpret_cast<uint16_t *>(&h); }
     RC_HD explicit h16(int v) : h16((float)v) {}
+    RC_HD explicit h16(unsigned int v) : h16((double)v) {}
     RC_HD explicit h16(long long v) : h16((double)v) {}
     RC_HD explicit h16(long v) : h16((double)v) {}
     RC_HD explicit h16(unsigned long v) : h16((double)v) {}
@@ -45,6 +46,7 @@ struct b16 {
     RC_HD explicit b16(float f) { __nv_bfloat16 h = __float2bfloat16_rn(f); bits = *reinterpret_cast<uint16_t *>(&h); }
     RC_HD explicit b16(double d) { __nv_bfloat16 h = __double2bfloat16(d); bits = *reinterpret_cast<uint16_t *>(&h); }
     RC_HD explicit b16(int v) : b16((float)v) {}
+    RC_HD explicit b16(unsigned int v) : b16((double)v) {}
     RC_HD explicit b16(long long v) : b16((double)v) {}
     RC_HD explicit b16(long v) : b16((double)v) {}
     RC_HD explicit b16(unsigned long v) : b16((double)v) {}
@@ -97,6 +99,7 @@ struct cplx {
     RC_HD cplx(R r, R i) : re(r), im(i) {}
     RC_HD explicit cplx(R r) : re(r), im((R)0) {}
     RC_HD explicit cplx(int v) : re((R)v), im((R)0) {}
+    RC_HD explicit cplx(unsigned int v) : re((R)v), im((R)0) {}
     RC_HD explicit cplx(long long v) : re((R)v), im((R)0) {}
     RC_HD explicit cplx(long v) : re((R)v), im((R)0) {}
     RC_HD explicit cplx(unsigned long v) : re((R)v), im((R)0) {}

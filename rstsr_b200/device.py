@@ -26,7 +26,15 @@ from ._ffi import CLayout, RstsrCudaError, byref, check
 _NP_TO_DT = {np.dtype(np.bool_): _ffi.BOOL, np.dtype(np.int8): _ffi.I8, np.dtype(np.int16): _ffi.I16,
              np.dtype(np.int32): _ffi.I32, np.dtype(np.int64): _ffi.I64, np.dtype(np.uint8): _ffi.U8,
              np.dtype(np.uint16): _ffi.U16, np.dtype(np.uint32): _ffi.U32, np.dtype(np.uint64): _ffi.U64,
-             np.dtype(np.float32): _ffi.F32, np.dtype(np.float64): _ffi.F64}
+             np.dtype(np.float32): _ffi.F32, np.dtype(np.float64): _ffi.F64,
+             # round 2: half and complex element types (half::f16, half::bf16, num::Complex<f32|f64>)
+             np.dtype(np.float16): _ffi.F16, np.dtype(np.complex64): _ffi.C32, np.dtype(np.complex128): _ffi.C64}
+try:  # bfloat16 has no NumPy dtype of its own; ml_dtypes provides one with the same f32-compute-round-once arithmetic
+    import ml_dtypes as _ml_dtypes
+    _NP_TO_DT[np.dtype(_ml_dtypes.bfloat16)] = _ffi.BF16
+    bfloat16 = _ml_dtypes.bfloat16
+except ImportError:  # pragma: no cover
+    bfloat16 = None
 _DT_TO_NP = {v: k for k, v in _NP_TO_DT.items()}
 
 
@@ -380,8 +388,8 @@ class DeviceCuda:
 
     def fill(self, c: CudaRaw, lc: Layout, value):
         v = np.array([value])
-        if v.dtype not in _NP_TO_DT:
-            v = v.astype(c.dtype)
+        if v.dtype not in _NP_TO_DT or c.dtype.kind == "c" or c.dtype.itemsize == 2 and c.dtype.kind not in "iu":
+            v = v.astype(c.dtype)  # half / complex targets: the host scalar arrives in the target type
         check(_ffi.lib().rc_fill(self._handle, dtype_code(c.dtype), c.ptr, byref(lc.to_c()), dtype_code(v.dtype),
                                  v.ctypes.data))
 

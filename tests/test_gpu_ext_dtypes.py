@@ -1,0 +1,238 @@
+"""GPU parity for the round-2 element types: half::f16, half::bf16, num::Complex<f32>, num::Complex<f64>
+(DeviceComplexFloatAPI, rstsr-core/src/operators/combined_trait.rs:6-55).
+
+Oracle = NumPy (float16, complex64 / complex128) and ml_dtypes.bfloat16, whose arithmetic is the `half` crate's: both
+operands to f32, the op, ONE rounding back.  Complex products / quotients are restated from num-complex's `impl Mul` /
+`impl Div` with separate real NumPy operations (NumPy's own complex loops may fuse or rescale).  Bit-exact for data
+movement, casts, + - * /, comparisons, conj / real / imag / square; libm-style functions within a half-precision ulp resp.
+1e-5 / 1e-13 for complex; reductions against an f64 / complex128 sum with the tolerance stated at the check."""
+import numpy as np
+import pytest
+
+import rstsr_b200 as rt
+from oracle import layout as L
+
+from helpers import P, seed_of, upload
+
+pytestmark = pytest.mark.gpu
+
+BF16 = rt.bfloat16
+HALF = [np.float16] + ([BF16] if BF16 is not None else [])
+CPLX = [np.complex64, np.complex128]
+ALL = HALF + CPLX
+
+
+def _name(dt):
+    return np.dtype(dt).name
+
+
+def _data(rng, n, dt, positive=False):
+    dt = np.dtype(dt)
+    if dt.kind == "c":
+        r = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        return r.astype(dt)
+    x = rng.standard_normal(n).astype(np.float32)
+    if positive:
+        x = np.abs(x) + np.float32(0.25)
+    return x.astype(dt)
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64,
+                   16: np.dtype([("lo", np.uint64), ("hi", np.uint64)])}[a.dtype.itemsize])
+
+
+def _same_bits(a, b):
+    return np.array_equal(_bits(a), _bits(b))
+
+
+@pytest.mark.parametrize("dt", ALL, ids=_name)
+def test_data_movement_is_bit_exact(dev, dt):
+    rng = np.random.default_rng(seed_of(("extmove", _name(dt))))
+    a = _data(rng, 70 * 130, dt)
+    t = rt.asarray(a, dev).reshape([70, 130])
+    assert _same_bits(t.to_numpy(), a.reshape(70, 130))
+    assert _same_bits(t.transpose([1, 0]).to_contig(rt.ROW_MAJOR).to_numpy(), a.reshape(70, 130).T)
+    assert _same_bits(t[3:60:2, ::-1].to_contig(rt.COL_MAJOR).to_numpy(), a.reshape(70, 130)[3:60:2, ::-1])
+    b = _data(rng, 12 * 66 * 68, dt).reshape(12, 66, 68)
+    tb = rt.asarray(b.reshape(-1), dev).reshape([12, 66, 68])
+    assert _same_bits(tb.transpose([2, 0, 1]).to_contig(rt.ROW_MAJOR).to_numpy(), b.transpose(2, 0, 1))
+    idx = [int(i) for i in rng.integers(0, 70, 33)]
+    assert _same_bits(t.index_select(0, idx).to_numpy(), a.reshape(70, 130)[idx])
+    val = (1.5 - 2j) if np.dtype(dt).kind == "c" else 1.5
+    assert _same_bits(rt.full([5, 7], val, dev, dtype=dt).to_numpy(), np.full((5, 7), val, dtype=dt))
+    assert _same_bits(rt.ones([9], dev, dtype=dt).to_numpy(), np.ones(9, dtype=dt))
+    assert _same_bits(rt.zeros([9], dev, dtype=dt).to_numpy(), np.zeros(9, dtype=dt))
+
+
+def test_casts(dev):
+    rng = np.random.default_rng(seed_of("extcast"))
+    x64 = rng.standard_normal(5000) * np.exp(rng.uniform(-12, 12, 5000))
+    x64[:6] = [0.0, -0.0, np.inf, -np.inf, np.nan, 65504.0]
+    x32 = x64.astype(np.float32)
+    pairs = [(np.float32, np.float16), (np.float64, np.float16), (np.float16, np.float32), (np.float16, np.float64)]
+    if BF16 is not None:
+        pairs += [(np.float32, BF16), (BF16, np.float32), (BF16, np.float64), (np.float16, BF16), (BF16, np.float16)]
+    for src, dst in pairs:
+        a = (x64 if np.dtype(src) == np.float64 else x32).astype(src)
+        got = rt.asarray(a, dev).astype(dst).to_numpy()
+        want = a.astype(np.float32).astype(dst) if np.dtype(src).itemsize == 2 else a.astype(dst)
+        assert _same_bits(got, want) or np.array_equal(got, want, equal_nan=True), (src, dst)
+    if BF16 is not None:  # f64 -> bf16 is ONE rounding (bf16::from_f64); ml_dtypes rounds through f32: allow the last bit
+        got = rt.asarray(x64, dev).astype(BF16).to_numpy().astype(np.float64)
+        want = x64.astype(np.float32).astype(BF16).astype(np.float64)
+        fin = np.isfinite(want)
+        assert np.all(np.abs(got[fin] - want[fin]) <= np.abs(want[fin]) * 2.0 ** -7)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+    for hdt in HALF:
+        b = rng.integers(0, 2, 300).astype(np.bool_)
+        assert _same_bits(rt.asarray(b, dev).astype(hdt).to_numpy(), b.astype(np.float32).astype(hdt))
+        h = _data(rng, 300, hdt)
+        h[:3] = np.array([0.0, -0.0, np.nan], dtype=np.float32).astype(hdt)
+        assert np.array_equal(rt.asarray(h, dev).astype(np.bool_).to_numpy(), h.astype(np.float32) != 0)
+    # real -> complex (a as R, 0) and complex <-> complex (componentwise `as`)
+    for src, dst in ((np.float32, np.complex64), (np.float64, np.complex128), (np.float32, np.complex128), (np.float64, np.complex64),
+                     (np.int32, np.complex128), (np.int64, np.complex128)):
+        a = (rng.standard_normal(400) * 100).astype(src)
+        got = rt.asarray(a, dev).astype(dst).to_numpy()
+        rdt = np.float32 if np.dtype(dst) == np.complex64 else np.float64
+        assert _same_bits(got.real.copy(), a.astype(rdt)) and not got.imag.any(), (src, dst)
+    z = _data(rng, 400, np.complex128)
+    assert _same_bits(rt.asarray(z, dev).astype(np.complex64).to_numpy(), z.astype(np.complex64))
+    z32 = z.astype(np.complex64)
+    assert _same_bits(rt.asarray(z32, dev).astype(np.complex128).to_numpy(), z32.astype(np.complex128))
+    with pytest.raises(rt.RstsrCudaError) as e:
+        rt.asarray(z, dev).astype(np.float64)   # the reference has no complex -> real DTypeCastAPI either
+    assert e.value.kind == "UnImplemented"
+
+
+def _cmul(a, b):
+    rdt = a.real.dtype
+    re = (a.real * b.real).astype(rdt) - (a.imag * b.imag).astype(rdt)
+    im = (a.real * b.imag).astype(rdt) + (a.imag * b.real).astype(rdt)
+    return (re + 1j * im).astype(a.dtype)
+
+
+def _cdiv(a, b):
+    rdt = a.real.dtype
+    n = (b.real * b.real).astype(rdt) + (b.imag * b.imag).astype(rdt)
+    re = ((a.real * b.real).astype(rdt) + (a.imag * b.imag).astype(rdt)) / n
+    im = ((a.imag * b.real).astype(rdt) - (a.real * b.imag).astype(rdt)) / n
+    return (re.astype(rdt) + 1j * im.astype(rdt)).astype(a.dtype)
+
+
+@pytest.mark.parametrize("dt", ALL, ids=_name)
+def test_arithmetic_bit_exact(dev, dt):
+    rng = np.random.default_rng(seed_of(("extarith", _name(dt))))
+    a, b = _data(rng, 48 * 80, dt).reshape(48, 80), _data(rng, 80, dt)
+    ta, tb = rt.asarray(a.reshape(-1), dev).reshape([48, 80]), rt.asarray(b, dev)
+    cplx = np.dtype(dt).kind == "c"
+    f32 = lambda x: x.astype(np.float32)
+    want = {"add": (a + b) if cplx else (f32(a) + f32(b)).astype(dt), "sub": (a - b) if cplx else (f32(a) - f32(b)).astype(dt),
+            "mul": _cmul(a, np.broadcast_to(b, a.shape)) if cplx else (f32(a) * f32(b)).astype(dt),
+            "div": _cdiv(a, np.broadcast_to(b, a.shape)) if cplx else (f32(a) / f32(b)).astype(dt)}
+    for op, w in want.items():
+        got = ta.binary(op, tb)
+        assert got.dtype == np.dtype(dt)
+        assert _same_bits(got.to_numpy(), w), (dt, op)
+    # transposed operand (tile kernel with 2- / 8- / 16-byte elements), scalar operand, in place
+    sq = _data(rng, 96 * 96, dt).reshape(96, 96)
+    tsq = rt.asarray(sq.reshape(-1), dev).reshape([96, 96])
+    w = (sq + sq.T) if cplx else (f32(sq) + f32(sq.T)).astype(dt)
+    assert _same_bits((tsq + tsq.transpose([1, 0])).to_numpy(), w)
+    s = np.array([0.75 - 0.5j if cplx else 0.75]).astype(dt)[0]
+    w = _cmul(a, np.full_like(a, s)) if cplx else (f32(a) * np.float32(s)).astype(dt)
+    assert _same_bits((ta * s).to_numpy(), w)
+    tc = rt.asarray(a.reshape(-1).copy(), dev).reshape([48, 80])
+    tc -= tb
+    assert _same_bits(tc.to_numpy(), want["sub"])
+    assert _same_bits((-ta).to_numpy(), -a)
+    # comparisons
+    eq = ta.binary("eq", ta).to_numpy()
+    assert eq.dtype == np.bool_ and eq.all()
+    assert np.array_equal(ta.binary("ne", tb).to_numpy(), a != b)
+    if not cplx:
+        for op, fn in (("lt", np.less), ("le", np.less_equal), ("gt", np.greater), ("ge", np.greater_equal)):
+            assert np.array_equal(ta.binary(op, tb).to_numpy(), fn(f32(a), f32(b))), (dt, op)
+        assert _same_bits(ta.binary("maximum", tb).to_numpy(), np.fmax(f32(a), f32(b)).astype(dt))
+        assert _same_bits(ta.binary("minimum", tb).to_numpy(), np.fmin(f32(a), f32(b)).astype(dt))
+    else:
+        with pytest.raises(rt.RstsrCudaError) as e:
+            ta.binary("lt", tb)
+        assert e.value.kind == "UnImplemented"
+
+
+@pytest.mark.parametrize("dt", HALF, ids=_name)
+def test_half_math_functions(dev, dt):
+    rng = np.random.default_rng(seed_of(("halfmath", _name(dt))))
+    x = _data(rng, 3000, dt, positive=True)
+    t = rt.asarray(x, dev)
+    ulp = 2.0 ** -9 if np.dtype(dt) == np.float16 else 2.0 ** -6
+    x32 = x.astype(np.float32)
+    for op, fn in (("sqrt", np.sqrt), ("exp", np.exp), ("log", np.log), ("sin", np.sin), ("cos", np.cos), ("tanh", np.tanh),
+                   ("reciprocal", lambda v: np.float32(1) / v), ("floor", np.floor), ("abs", np.abs), ("square", np.square)):
+        got = t.unary(op).to_numpy().astype(np.float64)
+        want = fn(x32).astype(dt).astype(np.float64)
+        assert np.allclose(got, want, rtol=ulp, atol=1e-7), (dt, op)
+    assert np.array_equal(t.unary("isnan").to_numpy(), np.isnan(x32))
+    pw = t.binary("pow", rt.asarray(_data(rng, 3000, dt), dev)).to_numpy().astype(np.float64)
+    assert np.all(np.isfinite(pw))
+
+
+@pytest.mark.parametrize("dt", CPLX, ids=_name)
+def test_complex_unary(dev, dt):
+    rng = np.random.default_rng(seed_of(("cplxun", _name(dt))))
+    z = _data(rng, 2500, dt)
+    t = rt.asarray(z, dev)
+    rdt = z.real.dtype
+    tol = 2e-6 if rdt == np.float32 else 1e-14
+    a = t.unary("abs")
+    assert a.dtype == rdt and np.allclose(a.to_numpy(), np.hypot(z.real, z.imag), rtol=tol, atol=0)
+    assert _same_bits(t.unary("real").to_numpy(), z.real.copy()) and _same_bits(t.unary("imag").to_numpy(), z.imag.copy())
+    assert _same_bits(t.unary("conj").to_numpy(), np.conj(z))
+    assert _same_bits(t.unary("square").to_numpy(), _cmul(z, z))
+    n = (z.real * z.real).astype(rdt) + (z.imag * z.imag).astype(rdt)
+    assert _same_bits(t.unary("reciprocal").to_numpy(), ((z.real / n).astype(rdt) + 1j * (-z.imag / n).astype(rdt)).astype(dt))
+    loose = 3e-5 if rdt == np.float32 else 1e-12
+    for op, fn in (("exp", np.exp), ("log", np.log), ("sqrt", np.sqrt), ("sin", np.sin), ("cos", np.cos), ("sinh", np.sinh),
+                   ("cosh", np.cosh), ("tanh", np.tanh)):
+        got = t.unary(op).to_numpy().astype(np.complex128)
+        want = fn(z.astype(np.complex128))
+        assert np.allclose(got, want, rtol=loose, atol=loose), (dt, op)
+    with pytest.raises(rt.RstsrCudaError):
+        t.unary("floor")
+
+
+@pytest.mark.parametrize("dt", ALL, ids=_name)
+def test_reductions(dev, dt):
+    rng = np.random.default_rng(seed_of(("extred", _name(dt))))
+    cplx = np.dtype(dt).kind == "c"
+    a = _data(rng, 300 * 257, dt).reshape(300, 257)
+    t = rt.asarray(a.reshape(-1), dev).reshape([300, 257])
+    wide = a.astype(np.complex128 if cplx else np.float64)
+    # one rounding to the element type on top of an f32 / element-precision accumulation
+    eps = {"float16": 2.0 ** -9, "bfloat16": 2.0 ** -6, "complex64": 1e-5, "complex128": 1e-12}[_name(dt)]
+    for axes in ([0], [1], [0, 1]):
+        got = t.sum_axes(axes).to_numpy().astype(wide.dtype)
+        want = wide.sum(axis=tuple(axes))
+        l1 = np.abs(wide).sum(axis=tuple(axes))
+        assert np.all(np.abs(got - want) <= eps * np.maximum(l1, np.abs(want)) + 1e-30), (dt, axes, "sum")
+        got = t.mean_axes(axes).to_numpy().astype(wide.dtype)
+        n = np.prod([a.shape[i] for i in axes])
+        assert np.all(np.abs(got - want / n) <= eps * np.maximum(l1 / n, np.abs(want / n)) + 1e-30), (dt, axes, "mean")
+    s = t.sum_all()
+    assert abs(complex(s) - complex(wide.sum())) <= eps * max(np.abs(wide).sum(), 1.0)
+    sm = (1 + 0.01 * _data(rng, 40, dt).astype(wide.dtype)).astype(dt)
+    p = complex(rt.asarray(sm, dev).prod_all())
+    pw = complex(np.prod(sm.astype(wide.dtype)))
+    assert abs(p - pw) <= 40 * eps * abs(pw)
+    if not cplx:
+        for axes in ([0], [1]):
+            assert _same_bits(t.max_axes(axes).to_numpy(), a.astype(np.float32).max(axis=axes[0]).astype(dt))
+            assert _same_bits(t.min_axes(axes).to_numpy(), a.astype(np.float32).min(axis=axes[0]).astype(dt))
+        assert float(t.max_all()) == float(a.astype(np.float32).max())
+    else:
+        with pytest.raises(rt.RstsrCudaError) as e:
+            t.max_all()
+        assert e.value.kind == "UnImplemented"
