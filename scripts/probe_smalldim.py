@@ -25,11 +25,11 @@ def timeit(fn, iters=8, warmup=2):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
-for tdt, ndt in ((torch.float64, np.float64), (torch.float32, np.float32)):
+for tdt, ndt in ((torch.float64, np.float64), (torch.float32, np.float32), (torch.int16, np.int16), (torch.uint8, np.uint8)):
     item = np.dtype(ndt).itemsize
     for k in (3, 4, 6, 8, 12, 16, 17, 24, 32, 48, 64, 100):
         n = (1 << 25) // k
-        src = torch.rand(k * n, dtype=tdt, device="cuda")
+        src = (torch.rand(k * n, device="cuda") * 100).to(tdt)
         dst = torch.empty(k * n, dtype=tdt, device="cuda")
         rs, rd = dev.wrap(src.data_ptr(), k * n, ndt), dev.wrap(dst.data_ptr(), k * n, ndt)
         # (k, n) row-major viewed transposed -> (n, k) contiguous output, and the other way round

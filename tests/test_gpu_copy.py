@@ -267,3 +267,25 @@ def test_narrow_permuted_copies(dev, dtype):
         idx = [slice(None)] * len(shape)
         v = a.reshape(shape).transpose(perm)[1:, 2:]
         assert np.array_equal(t2.to_numpy(), np.ascontiguousarray(v)), (dtype, shape, perm, "sliced")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32, np.int16, np.uint8])
+def test_short_axis_packed_transposes(dev, dtype):
+    """(n, k) <-> (k, n) copies of <= 4-byte elements with a packed short axis take the strip kernel
+    (rc_tile_strip.cuh) in both directions; unpacked (sliced) operands fall back to the rectangular / square tile."""
+    rng = np.random.default_rng(seed_of(("strip", np.dtype(dtype).name)))
+    for k in (2, 3, 5, 8, 17, 31, 64):
+        for n in (1024, 5003):
+            a = rng.integers(0, 120, n * k).astype(dtype)
+            # short Y: source rows of k elements packed -> k long output rows
+            t = rt.Tensor(upload(dev, a), rt.Layout((k, n), (1, k))).to_contig(rt.ROW_MAJOR)
+            assert np.array_equal(t.to_numpy(), a.reshape(n, k).T), (dtype, k, n, "short y")
+            # short X: k long source rows -> output rows of k elements packed
+            t = rt.Tensor(upload(dev, a), rt.Layout((n, k), (1, n))).to_contig(rt.ROW_MAJOR)
+            assert np.array_equal(t.to_numpy(), a.reshape(k, n).T), (dtype, k, n, "short x")
+    # batched, and a sliced source whose short rows are NOT packed
+    a = rng.integers(0, 120, 3 * 4000 * 6).astype(dtype)
+    t = rt.Tensor(upload(dev, a), rt.Layout((3, 6, 4000), (24000, 1, 6))).to_contig(rt.ROW_MAJOR)
+    assert np.array_equal(t.to_numpy(), a.reshape(3, 4000, 6).transpose(0, 2, 1))
+    t = rt.Tensor(upload(dev, a), rt.Layout((5, 4000), (1, 6), 1)).to_contig(rt.ROW_MAJOR)
+    assert np.array_equal(t.to_numpy(), a[:24000].reshape(4000, 6)[:, 1:6].T)
