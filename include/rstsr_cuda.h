@@ -66,7 +66,8 @@ typedef enum rc_dtype {
      * textbook formulas of num-complex.  Covered: storage, copy / to_contig / gather (raw words), fill, casts
      * half <-> f32 / f64 / bool and real -> complex, c32 <-> c64; + - * / neg, comparisons (== != only for complex),
      * maximum / minimum and the float math functions for half; abs / real / imag (real output), conj, square, exp, log,
-     * sqrt, sin, cos, sinh, cosh, tanh, reciprocal for complex; sum / prod / mean (all four), max / min (half).
+     * sqrt, sin, cos, sinh, cosh, tanh, reciprocal for complex; reductions sum / prod / mean / var / std / l2_norm (all
+     * four; var / std / l2_norm of complex are real), max / min / argmin / argmax / count_nonzero (half).
      * Anything else on these types is RC_ERR_UNIMPLEMENTED. */
     RC_F16 = 11,
     RC_BF16 = 12,

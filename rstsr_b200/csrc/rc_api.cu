@@ -81,6 +81,8 @@ void run_reduce_i16(rc_device *, rc_redop, const CanonRed &, const void *, void 
 void run_reduce_u16(rc_device *, rc_redop, const CanonRed &, const void *, void *, int64_t);
 
 rc_dtype redop_out_dtype(rc_redop op, rc_dtype t) {
+    // var / std / l2_norm of a complex tensor are real (TOut = T::Real, auto_impl/reduction.rs:213,267,323)
+    if (dtype_is_complex(t) && (op == RC_VAR || op == RC_STD || op == RC_L2_NORM)) return t == RC_C32 ? RC_F32 : RC_F64;
     switch (op) {
         case RC_ARGMIN: case RC_ARGMAX: case RC_COUNT_NONZERO: return RC_U64;
         case RC_ALL: case RC_ANY: return RC_BOOL;
@@ -219,7 +221,7 @@ void reduce_into_nolock(rc_device *dev, rc_redop op, rc_dtype t, const void *a, 
     if (op == RC_MEAN)
         RC_CHECK(dtype_is_float(t) || dtype_is_extended(t), RC_ERR_UNIMPLEMENTED, "mean requires a floating-point dtype");
     if (op == RC_VAR || op == RC_STD || op == RC_L2_NORM)
-        RC_CHECK(dtype_is_float(t), RC_ERR_UNIMPLEMENTED, "var / std / l2_norm require f32 or f64");
+        RC_CHECK(dtype_is_float(t) || dtype_is_extended(t), RC_ERR_UNIMPLEMENTED, "var / std / l2_norm require a floating-point dtype");
     if (op == RC_ALL || op == RC_ANY) RC_CHECK(t == RC_BOOL, RC_ERR_UNIMPLEMENTED, "all / any take a bool tensor");
     const bool arg = (op == RC_ARGMIN || op == RC_ARGMAX);
     if (arg)  // reduce_all_unraveled_arg_cpu_serial: "empty sequence is not allowed for reduce_arg."

@@ -1,46 +1,88 @@
-// rc_reduce_extx.cu -- sum / prod / mean (f16, bf16, c32, c64) and max / min (f16, bf16) on the reduction kernels of
-// rc_reduce.cuh.  Half inputs are accumulated in f32 and rounded ONCE at the end (the reference accumulates in the
-// element type, `acc + x` in half precision: our result is the more accurate one and lies within half-precision
-// rounding of it; tests compare against an f64 sum with 2^-9 / 2^-6 relative tolerance for f16 / bf16).  Complex sums
-// are componentwise; the complex mean divides by Complex::from(n) with the same division formula the operators use.
+// rc_reduce_extx.cu -- reductions of the extended element types (f16, bf16, c32, c64) on the kernels of rc_reduce.cuh.
+//   half     every policy of the f32 path through PViaF32: inputs converted to f32, f32 state, ONE rounding of the result
+//            (sum / prod / max / min / mean / var / std / l2_norm), index / count outputs unchanged (argmin / argmax /
+//            count_nonzero).  The reference accumulates in the element type (`acc + x` in half precision): ours is the
+//            more accurate value and lies within half-precision rounding of it.
+//   complex  sum / prod / mean componentwise resp. with the operators of rc_types.cuh (the mean divides by
+//            Complex::from(n)); var / std / l2_norm with REAL output as auto_impl/reduction.rs:207-354 defines them:
+//            state (sum x, sum (x * conj x).re), var = q / n - (m * conj m).re with m = s / Complex::from(n).
 #include "rc_reduce.cuh"
 #include "rc_types.cuh"
 
 namespace rc {
 namespace {
 
-// half input, f32 state, half output; the second pass folds f32 states (PState)
-template <class T, template <class> class PF>
+// half input through a policy PF of the f32 path; outputs of type float become the half type again
+template <class T, class PF>
 struct PViaF32 {
-    using TI = T; using S = float; using TO = T; using Second = PState<PViaF32<T, PF>>;
-    static __device__ __forceinline__ S init() { return PF<float>::init(); }
-    static __device__ __forceinline__ S pre(T x, int64_t) { return x.f(); }
-    static __device__ __forceinline__ S comb(S a, S b) { return PF<float>::comb(a, b); }
-    static __device__ __forceinline__ TO fin(S s, int64_t n) { return T(PF<float>::fin(s, n)); }
+    using TI = T;
+    using S = typename PF::S;
+    using TO = typename std::conditional<std::is_same<typename PF::TO, float>::value, T, typename PF::TO>::type;
+    using Second = PState<PViaF32<T, PF>>;
+    static __device__ __forceinline__ S init() { return PF::init(); }
+    static __device__ __forceinline__ S pre(T x, int64_t idx) { return PF::pre(x.f(), idx); }
+    static __device__ __forceinline__ S comb(S a, S b) { return PF::comb(a, b); }
+    static __device__ __forceinline__ TO fin(S s, int64_t n) {
+        if constexpr (std::is_same<typename PF::TO, float>::value) return T(PF::fin(s, n));
+        else return PF::fin(s, n);
+    }
+};
+
+template <class R> struct alignas(4 * sizeof(R)) CVarState { cplx<R> s; R q; R pad; };  // 16 / 32 bytes: one LDG
+template <class R, bool STD> struct PCVar {
+    using TI = cplx<R>; using S = CVarState<R>; using TO = R; using Second = PState<PCVar<R, STD>>;
+    static __device__ __forceinline__ S init() { return S{cplx<R>((R)0, (R)0), (R)0, (R)0}; }
+    static __device__ __forceinline__ S pre(TI x, int64_t) { return S{x, x.re * x.re + x.im * x.im, (R)0}; }
+    static __device__ __forceinline__ S comb(S a, S b) { return S{a.s + b.s, a.q + b.q, (R)0}; }
+    static __device__ __forceinline__ TO fin(S v, int64_t n) {
+        const cplx<R> mean = v.s / cplx<R>((R)n, (R)0);
+        const R var = v.q / (R)n - (mean.re * mean.re + mean.im * mean.im);
+        if constexpr (!STD) return var;
+        else if constexpr (sizeof(R) == 4) return sqrtf(var);
+        else return sqrt(var);
+    }
+};
+template <class R> struct PCL2 {
+    using TI = cplx<R>; using S = R; using TO = R; using Second = PState<PCL2<R>>;
+    static __device__ __forceinline__ S init() { return (R)0; }
+    static __device__ __forceinline__ S pre(TI x, int64_t) { return x.re * x.re + x.im * x.im; }
+    static __device__ __forceinline__ S comb(S a, S b) { return a + b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { if constexpr (sizeof(R) == 4) return sqrtf(s); else return sqrt(s); }
 };
 
 template <class T>
 void reduce_half(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, void *out, int64_t n) {
     switch (op) {
-        case RC_SUM: reduce_typed<PViaF32<T, PSum>>(dev, c, a, out, n); return;
-        case RC_PROD: reduce_typed<PViaF32<T, PProd>>(dev, c, a, out, n); return;
-        case RC_MAX: reduce_typed<PViaF32<T, PMax>>(dev, c, a, out, n); return;
-        case RC_MIN: reduce_typed<PViaF32<T, PMin>>(dev, c, a, out, n); return;
-        case RC_MEAN: reduce_typed<PViaF32<T, PMean>>(dev, c, a, out, n); return;
+        case RC_SUM: reduce_typed<PViaF32<T, PSum<float>>>(dev, c, a, out, n); return;
+        case RC_PROD: reduce_typed<PViaF32<T, PProd<float>>>(dev, c, a, out, n); return;
+        case RC_MAX: reduce_typed<PViaF32<T, PMax<float>>>(dev, c, a, out, n); return;
+        case RC_MIN: reduce_typed<PViaF32<T, PMin<float>>>(dev, c, a, out, n); return;
+        case RC_MEAN: reduce_typed<PViaF32<T, PMean<float>>>(dev, c, a, out, n); return;
+        case RC_VAR: reduce_typed<PViaF32<T, PVar<float, false>>>(dev, c, a, out, n); return;
+        case RC_STD: reduce_typed<PViaF32<T, PVar<float, true>>>(dev, c, a, out, n); return;
+        case RC_L2_NORM: reduce_typed<PViaF32<T, PL2<float>>>(dev, c, a, out, n); return;
+        case RC_ARGMIN: reduce_typed<PViaF32<T, PArg<float, false>>>(dev, c, a, out, n); return;
+        case RC_ARGMAX: reduce_typed<PViaF32<T, PArg<float, true>>>(dev, c, a, out, n); return;
+        case RC_COUNT_NONZERO: reduce_typed<PViaF32<T, PCount<float>>>(dev, c, a, out, n); return;
         default: break;
     }
     raise(RC_ERR_UNIMPLEMENTED, "this reduction is not implemented for half types");
 }
 
-template <class T>
+template <class R>
 void reduce_cplx(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, void *out, int64_t n) {
+    using T = cplx<R>;
     switch (op) {
         case RC_SUM: reduce_typed<PSum<T>>(dev, c, a, out, n); return;
         case RC_PROD: reduce_typed<PProd<T>>(dev, c, a, out, n); return;
         case RC_MEAN: reduce_typed<PMean<T>>(dev, c, a, out, n); return;
+        case RC_VAR: reduce_typed<PCVar<R, false>>(dev, c, a, out, n); return;
+        case RC_STD: reduce_typed<PCVar<R, true>>(dev, c, a, out, n); return;
+        case RC_L2_NORM: reduce_typed<PCL2<R>>(dev, c, a, out, n); return;
         default: break;
     }
-    raise(RC_ERR_UNIMPLEMENTED, "complex numbers have sum / prod / mean only (no ordering, ExtReal is not implemented for them)");
+    raise(RC_ERR_UNIMPLEMENTED, "complex numbers have no ordering: max / min / argmin / argmax are not defined for them "
+                                "(ExtReal is not implemented for Complex)");
 }
 
 }  // namespace
@@ -49,8 +91,8 @@ void run_reduce_extx(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr
     switch (t) {
         case RC_F16: reduce_half<h16>(dev, op, cr, a, out, n); return;
         case RC_BF16: reduce_half<b16>(dev, op, cr, a, out, n); return;
-        case RC_C32: reduce_cplx<c32>(dev, op, cr, a, out, n); return;
-        case RC_C64: reduce_cplx<c64>(dev, op, cr, a, out, n); return;
+        case RC_C32: reduce_cplx<float>(dev, op, cr, a, out, n); return;
+        case RC_C64: reduce_cplx<double>(dev, op, cr, a, out, n); return;
         default: break;
     }
     raise(RC_ERR_INVALID_VALUE, "not an extended dtype");

@@ -236,3 +236,40 @@ def test_reductions(dev, dt):
         with pytest.raises(rt.RstsrCudaError) as e:
             t.max_all()
         assert e.value.kind == "UnImplemented"
+
+
+@pytest.mark.parametrize("dt", ALL, ids=_name)
+def test_var_std_l2_and_arg_reductions(dev, dt):
+    """var / std / l2_norm (REAL output for complex: TOut = T::Real, auto_impl/reduction.rs:207-354); for the half types
+    also argmin / argmax / count_nonzero.  Values against f64 / complex128 NumPy with the element type's rounding."""
+    rng = np.random.default_rng(seed_of(("extvar", _name(dt))))
+    cplx = np.dtype(dt).kind == "c"
+    a = _data(rng, 120 * 96, dt).reshape(120, 96)
+    t = rt.asarray(a.reshape(-1), dev).reshape([120, 96])
+    wide = a.astype(np.complex128 if cplx else np.float64)
+    out_dt = a.real.dtype if cplx else np.dtype(dt)
+    eps = {"float16": 2.0 ** -8, "bfloat16": 2.0 ** -5, "complex64": 2e-5, "complex128": 1e-12}[_name(dt)]
+    for axes in ([0], [1], [0, 1]):
+        ax = tuple(axes)
+        n = np.prod([a.shape[i] for i in axes])
+        want_var = (np.abs(wide) ** 2).sum(axis=ax) / n - np.abs(wide.sum(axis=ax) / n) ** 2
+        got = t.var_axes(axes)
+        assert got.dtype == out_dt
+        assert np.allclose(got.to_numpy().astype(np.float64), want_var, rtol=4 * eps, atol=4 * eps), (dt, axes, "var")
+        assert np.allclose(t.std_axes(axes).to_numpy().astype(np.float64), np.sqrt(want_var), rtol=4 * eps, atol=4 * eps), (dt, axes, "std")
+        want_l2 = np.sqrt((np.abs(wide) ** 2).sum(axis=ax))
+        got = t.l2_norm_axes(axes)
+        assert got.dtype == out_dt and np.allclose(got.to_numpy().astype(np.float64), want_l2, rtol=2 * eps, atol=0), (dt, axes, "l2")
+    assert abs(float(t.l2_norm_all()) - float(np.sqrt((np.abs(wide) ** 2).sum()))) <= 2 * eps * float(np.sqrt((np.abs(wide) ** 2).sum()))
+    if not cplx:
+        a32 = a.astype(np.float32)
+        assert np.array_equal(t.argmax_axes([1]).to_numpy(), a32.argmax(axis=1).astype(np.uint64))
+        assert np.array_equal(t.argmin_axes([0]).to_numpy(), a32.argmin(axis=0).astype(np.uint64))
+        assert int(t.argmax_all()) == int(a32.argmax())
+        z = a.copy()
+        z[::3] = np.zeros(1, dtype=dt)[0]
+        assert int(rt.asarray(z.reshape(-1), dev).reshape([120, 96]).count_nonzero_all()) == int(np.count_nonzero(z.astype(np.float32)))
+    else:
+        with pytest.raises(rt.RstsrCudaError) as e:
+            t.argmax_all()
+        assert e.value.kind == "UnImplemented"
