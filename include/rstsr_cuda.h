@@ -21,6 +21,15 @@
  *
  * There is NO CPU fallback: if the CUDA runtime or a device is unavailable every
  * compute entry point fails with RC_ERR_DEVICE.
+ *
+ * Environment variables (read once per process; experiments only -- every default is the measured best and none
+ * changes a result; DESIGN.md "Tuning knobs" has the sweeps behind them):
+ *   RC_TILE_MIN_X / RC_TILE_MIN_Y, RC_TILE_RECT, RC_RECT_MAX_Y8 / _Y4, RC_RECT_X_LO8 / HI8 / LO4 / HI4   tile-kernel selection
+ *   RC_TILE_BULK (0)      1: eligible 8-byte permuted copies take the TMA kernel (cp.async.bulk.tensor)
+ *   RC_TILE_NARROW (1), RC_EW_OUTER (1), RC_SEL_WINDOW (1)   0: 1-/2-byte word tile, outer kernel, windowed gather off
+ *   RC_ROWS_PER_CTA (1), RC_TCOL_MAX (64), RC_COLS_MIN (2), RC_TRI_TILE / RC_UNPACK_TILE (64)
+ *   RC_COMM_PEER (1)      0: sharded reductions use ncclAllReduce for every size (no NVLink peer window)
+ *   RC_COMM_TIMEOUT_S (120)   bound of the in-kernel wait for a lost rank in the peer-window exchange
  */
 #ifndef RSTSR_CUDA_H
 #define RSTSR_CUDA_H
