@@ -439,7 +439,7 @@ def run_product(args, rank, local_rank, world):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        traffic = tj.get("ew_tile_kernel_cfg2_bytes")
+        traffic = tj.get("ew_tile_wide_kernel_cfg2_bytes", tj.get("ew_tile_kernel_cfg2_bytes"))
         traffic_src = tj.get("source")
     except Exception:
         pass
@@ -455,7 +455,7 @@ def run_product(args, rank, local_rank, world):
         "pct_of_measured_peak": round(value / world / peak * 100, 1),
         "per_op": per_op,
         "per_config": per_config,
-        "roofline": {"bound": "hbm", "kernel": "ew_tile_kernel<FIdentity<u64>> (cfg2 permuted copy)",
+        "roofline": {"bound": "hbm", "kernel": "ew_tile_wide_kernel<u64, 128, 32, 256> (cfg2 permuted copy)",
                      "achieved": dom["gbs"], "peak": peak, "peak_kind": peak_kind + " (burst copy, MEASURED_PEAKS.json)",
                      "unit": "GB/s", "frac": round(dom["gbs"] / peak, 4), "traffic": traffic,
                      "traffic_source": traffic_src, "algorithmic_bytes": BYTES_CFG2},

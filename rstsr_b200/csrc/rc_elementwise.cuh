@@ -457,7 +457,116 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) ew_tile_kernel(const __grid_c
 }  // namespace rc
 #include "rc_tile_bulk.cuh"
 #include "rc_tile_narrow.cuh"
+#include "rc_tile_wide.cuh"
+#include "rc_tile_short.cuh"
 namespace rc {
+
+template <class F> struct is_word_copy : std::false_type {};
+template <> struct is_word_copy<FIdentity<uint8_t>> : std::true_type {};
+template <> struct is_word_copy<FIdentity<uint16_t>> : std::true_type {};
+template <> struct is_word_copy<FIdentity<uint32_t>> : std::true_type {};
+template <> struct is_word_copy<FIdentity<uint64_t>> : std::true_type {};
+
+// RC_TILE_SHORT=0 switches ew_tile_short_kernel off; RC_SHORT_MAX_K<S> = longest short extent of S-byte elements it takes
+inline bool tile_short_enabled() {
+    static bool v = [] { const char *e = getenv("RC_TILE_SHORT"); return !(e && e[0] == '0'); }();
+    return v;
+}
+inline int tile_short_max_k(size_t esz) {
+    auto knob = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    // above these the tile no longer fits one trip of loads and the partly filled square / word tile is faster
+    // (profiles/r02_tile_short.md)
+    static const int m1 = knob("RC_SHORT_MAX_K1", 64), m2 = knob("RC_SHORT_MAX_K2", 48),
+                     m4 = knob("RC_SHORT_MAX_K4", 40), m8 = knob("RC_SHORT_MAX_K8", 32);
+    return std::min<int>(SHORT_MAX_K, esz == 1 ? m1 : esz == 2 ? m2 : esz == 4 ? m4 : m8);
+}
+
+// kind 1: short Y, flat source (de-interleave); kind 2: short X, flat output (interleave).  `t` is the TileDesc of a staged
+// one-operand copy (slot 0 = output, slot 1 = source).
+template <int S, class TD>
+bool launch_tile_short(rc_device *dev, const TD &t, int kind, void *pc, const void *pa) {
+    ShortDesc d;
+    std::memset(&d, 0, sizeof(d));
+    const bool deint = kind == 1;
+    d.k = deint ? t.ny : t.nx;
+    d.n = deint ? t.nx : t.ny;
+    d.srow = deint ? t.sy[0] : t.sx[1];
+    const int fs = deint ? 1 : 0, rs = deint ? 0 : 1;  // slots of the flat side and of the rows side
+    constexpr int VE = 16 / S;
+    bool vec = d.n % VE == 0 && d.srow % VE == 0 && reinterpret_cast<uintptr_t>(pc) % 16 == 0 &&
+               reinterpret_cast<uintptr_t>(pa) % 16 == 0;
+    d.nbatch = t.nbatch;
+    int64_t nb = 1;
+    for (int i = 0; i < t.nbatch; ++i) {
+        d.bdiv[i] = t.bdiv[i];
+        d.bstride_flat[i] = t.bstride[fs][i];
+        d.bstride_rows[i] = t.bstride[rs][i];
+        vec = vec && t.bstride[0][i] % VE == 0 && t.bstride[1][i] % VE == 0;
+        nb *= t.bdiv[i].d;
+    }
+    // tile: R long positions, a multiple of 32 units (unit = VE positions = k * 16 bytes), payload <= 20 KB so that all
+    // of a tile's loads are in flight at once and 8 CTAs fit an SM (profiles/r02_tile_short.md: larger tiles lose 15-20 %)
+    static const uint64_t tile_bytes = [] { const char *e = getenv("RC_SHORT_TILE_BYTES"); return e ? (uint64_t)atoll(e) : (uint64_t)SHORT_TILE_BYTES; }();
+    const uint32_t g = 32 * VE;
+    uint32_t R = (uint32_t)(tile_bytes / ((uint64_t)d.k * S) / g) * g;
+    R = std::max<uint32_t>(g, std::min<uint32_t>(R, (d.n + g - 1) / g * g));
+    d.R = R;
+    d.div_k = FastDiv(d.k);
+    d.div_ch = FastDiv(R / (32 * (vec ? VE : 1)));
+    d.tiles = (d.n + R - 1) / R;
+    d.div_tiles = FastDiv(d.tiles);
+    const int64_t total = (int64_t)d.tiles * nb;
+    if (total >= (1ll << 31)) return false;
+    d.total = (uint32_t)total;
+    const size_t smem = (size_t)(R / VE) * (16 * d.k + (S == 8 ? 8 : 4)) + 16;
+    unsigned char *flat = deint ? static_cast<unsigned char *>(const_cast<void *>(pa)) : static_cast<unsigned char *>(pc);
+    unsigned char *rows = deint ? static_cast<unsigned char *>(pc) : static_cast<unsigned char *>(const_cast<void *>(pa));
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<d.total, SHORT_THREADS, smem, dev->stream>>>(d, flat, rows);
+    };
+    if (vec) { if (deint) go(ew_tile_short_kernel<S, true, true>); else go(ew_tile_short_kernel<S, true, false>); }
+    else { if (deint) go(ew_tile_short_kernel<S, false, true>); else go(ew_tile_short_kernel<S, false, false>); }
+    after_launch(dev, "ew_tile_short_kernel");
+    return true;
+}
+
+// RC_TILE_WIDE=0: 8-byte permuted copies stay on the square 64 x 64 tile (default: the 128 x 32 tile of rc_tile_wide.cuh)
+inline bool tile_wide_enabled() {
+    static bool v = [] { const char *e = getenv("RC_TILE_WIDE"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+template <class T, int TX, int TY, int NT, class TD>
+bool launch_tile_wide(rc_device *dev, const TD &t, T *pc, const T *pa) {
+    WideDesc w;
+    std::memset(&w, 0, sizeof(w));
+    w.nx = t.nx;
+    w.ny = t.ny;
+    w.tiles_x = (t.nx + TX - 1) / TX;
+    w.tiles_y = (t.ny + TY - 1) / TY;
+    w.div_tx = FastDiv(w.tiles_x);
+    w.div_ty = FastDiv(w.tiles_y);
+    w.nbatch = t.nbatch;
+    int64_t nb = 1;
+    for (int i = 0; i < t.nbatch; ++i) {
+        w.bdiv[i] = t.bdiv[i];
+        w.bstride_c[i] = t.bstride[0][i];
+        w.bstride_a[i] = t.bstride[1][i];
+        nb *= t.bdiv[i].d;
+    }
+    w.sx_a = t.sx[1];
+    w.sy_c = t.sy[0];
+    const int64_t tiles = (int64_t)w.tiles_x * w.tiles_y * nb;
+    if (tiles >= (1ll << 31)) return false;
+    w.total_tiles = (uint32_t)tiles;
+    const size_t smem = sizeof(T) * TX * (TY + 1);
+    if (smem > 48 * 1024)
+        RC_CUDA(cudaFuncSetAttribute(ew_tile_wide_kernel<T, TX, TY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ew_tile_wide_kernel<T, TX, TY, NT><<<w.total_tiles, NT, smem, dev->stream>>>(w, pc, pa);
+    after_launch(dev, "ew_tile_wide_kernel");
+    return true;
+}
 
 // RC_EW_OUTER=0 keeps write-only outer ops on the flat kernel (experiments)
 inline bool outer_enabled() {
@@ -798,6 +907,16 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
         // the square tile needs both extents above its thresholds; the rectangular one takes its own shapes
         const bool square_x_ok = c.shape[0] >= tile_min_x(sizeof(TO));
         const uint32_t nx32 = (uint32_t)std::min<int64_t>(c.shape[0], 1u << 30);
+        // a one-operand word copy with one short extent whose side is flat: ew_tile_short_kernel (rc_tile_short.cuh)
+        auto short_kind = [&](int s, int i) -> int {
+            if constexpr (NIN == 1 && is_word_copy<F>::value) {
+                if (!tile_short_enabled() || s < 0) return 0;
+                const int64_t nx = c.shape[0], ny = c.shape[i], kmax = tile_short_max_k(sizeof(TO));
+                if (ny >= 2 && ny <= kmax && nx >= RECT_LONG && nx < (1ll << 31) && c.stride[s][0] == ny) return 1;
+                if (nx >= 2 && nx <= kmax && ny >= RECT_LONG && ny < (1ll << 31) && c.stride[0][i] == nx) return 2;
+            }
+            return 0;
+        };
         auto unit_dim = [&](int s) {
             if (s < 0) return -1;
             if (c.stride[s][0] == 0 || c.stride[s][0] == 1) return -1;  // already fine along X
@@ -805,6 +924,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
             for (int i = 1; i < c.ndim; ++i) {
                 if (c.stride[s][i] != 1) continue;
                 const uint32_t ny32 = (uint32_t)std::min<int64_t>(c.shape[i], 1u << 30);
+                if (short_kind(s, i)) return i;
                 if ((square_x_ok && c.shape[i] >= tile_min_y(esz)) || rect_short_y(nx32, ny32, esz) ||
                     rect_short_x(nx32, ny32, sizeof(TO)))
                     return i;
@@ -843,6 +963,11 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                 int tm_a = TILE_CONST, tm_b = TILE_CONST;
                 if (slot_a >= 0) tm_a = (c.stride[slot_a][ydim] == 1 && c.stride[slot_a][0] > 1 && ya == ydim) ? TILE_STAGED : TILE_DIRECT;
                 if (slot_b >= 0) tm_b = (c.stride[slot_b][ydim] == 1 && c.stride[slot_b][0] > 1 && yb == ydim) ? TILE_STAGED : TILE_DIRECT;
+                // word copy, one short extent on a flat side
+                if constexpr (NIN == 1 && is_word_copy<F>::value) {
+                    const int kind = tm_a == TILE_STAGED ? short_kind(slot_a, ydim) : 0;
+                    if (kind && launch_tile_short<(int)sizeof(TO)>(dev, t, kind, pc, pa)) return;
+                }
                 // one short and one long extent: rectangular tile, the short extent taken whole
                 const size_t esz_staged = (ya == ydim && slot_a >= 0) ? sizeof(TA) : sizeof(TB);
                 if constexpr (sizeof(TA) <= 8 && sizeof(TB) <= 8 && sizeof(TO) <= 8)  // 16-byte elements (c64): square tile only
@@ -924,6 +1049,12 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
                             return;
                         }
                     }
+                }
+                // 8-byte permuted COPY, both extents large: wide tile (longer write runs; rc_tile_wide.cuh)
+                if constexpr (NIN == 1 && std::is_same<F, FIdentity<uint64_t>>::value) {
+                    if (tile_wide_enabled() && tm_a == TILE_STAGED && t.sx[0] == 1 && t.sy[1] == 1 && t.nx >= 256 && t.ny >= 64 &&
+                        tile_bulk_mode() != 1 && launch_tile_wide<TO, 128, 32, 256>(dev, t, pc, pa))
+                        return;
                 }
                 // 8-byte permuted COPY of whole 64 x 64 tiles: the TMA kernel (rc_tile_bulk.cuh) where the tensor maps exist
                 if constexpr (NIN == 1 && std::is_same<F, FIdentity<uint64_t>>::value) {

@@ -60,7 +60,7 @@ def main():
     except Exception:
         pass
     prev_source = traffic.pop("source", None)
-    names = {f"{RND}_tile_cfg2.ncu-rep": "ew_tile_kernel_cfg2_bytes", f"{RND}_rows_cfg1.ncu-rep": "ew_rows_kernel_cfg1_bytes",
+    names = {f"{RND}_wide_cfg2.ncu-rep": "ew_tile_wide_kernel_cfg2_bytes", f"{RND}_tile_cfg2.ncu-rep": "ew_tile_kernel_cfg2_bytes", f"{RND}_rows_cfg1.ncu-rep": "ew_rows_kernel_cfg1_bytes",
              f"{RND}_redrows_cfg3.ncu-rep": "reduce_rows_kernel_cfg3_bytes", f"{RND}_cols_cfg3.ncu-rep": "reduce_cols_kernel_cfg3_bytes"}
     for rep, key in names.items():
         if rep in full:

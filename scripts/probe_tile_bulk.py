@@ -16,6 +16,8 @@ from rstsr_b200 import Layout
 
 dev = rt.DeviceCuda(0, rt.ROW_MAJOR, stream=torch.cuda.current_stream().cuda_stream)
 mode = os.environ.get("RC_TILE_BULK", "default")
+if os.environ.get("RC_TILE_WIDE"):
+    mode = "wide" + os.environ["RC_TILE_WIDE"]
 g = torch.Generator(device="cuda"); g.manual_seed(3)
 rows = []
 

@@ -1,7 +1,8 @@
 """ncu driver for the round-2 kernels: one shape per case, a few launches, nothing else on the stream.
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 2 -c 1 -o gpurun_out/r02_<case> python scripts/run_r02_shapes.py <case>
 cases: narrow_u8, narrow_i16 (ew_tile_narrow_kernel), outer_f64 (ew_outer_kernel), cast_u8_f32 (ew_kernel, packs),
-       tma_cfg2 (ew_tile_tma_kernel, needs RC_TILE_BULK=1), tile_cfg2 (ew_tile_kernel)"""
+       tma_cfg2 (ew_tile_tma_kernel, needs RC_TILE_BULK=1), tile_cfg2 (ew_tile_kernel, needs RC_TILE_WIDE=0),
+       wide_cfg2 (ew_tile_wide_kernel), short_{f32,u8}_{deint,inter} (ew_tile_short_kernel)"""
 import os
 import sys
 
@@ -50,6 +51,13 @@ elif case == "cast_u8_f32":
     ra, rb = dev.wrap(a.data_ptr(), n, np.uint8), dev.wrap(b.data_ptr(), n, np.float32)
     for _ in range(4):
         dev.assign(rb, Layout((n,), (1,)), ra, Layout((n,), (1,)))
+elif case == "wide_cfg2":      # ew_tile_wide_kernel (default for 8-byte permuted copies)
+    transpose_copy(torch.float64, np.float64, (1024, 1024, 512), (2, 0, 1))
+elif case in ("short_f32_deint", "short_f32_inter", "short_u8_deint", "short_u8_inter"):  # ew_tile_short_kernel
+    tdt, ndt = (torch.float32, np.float32) if "f32" in case else (torch.uint8, np.uint8)
+    k = 8 if "f32" in case else 3
+    n = ((1 << 28) // (k * np.dtype(ndt).itemsize) // 16) * 16 + 16
+    transpose_copy(tdt, ndt, (n, k) if "deint" in case else (k, n), (1, 0))
 else:
     raise SystemExit(f"unknown case {case}")
 torch.cuda.synchronize()

@@ -269,23 +269,36 @@ def test_narrow_permuted_copies(dev, dtype):
         assert np.array_equal(t2.to_numpy(), np.ascontiguousarray(v)), (dtype, shape, perm, "sliced")
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.int32, np.int16, np.uint8])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int32, np.int16, np.uint8])
 def test_short_axis_packed_transposes(dev, dtype):
-    """(n, k) <-> (k, n) copies of <= 4-byte elements with a packed short axis take the strip kernel
-    (rc_tile_strip.cuh) in both directions; unpacked (sliced) operands fall back to the rectangular / square tile."""
+    """(n, k) <-> (k, n) word copies with a packed short axis take ew_tile_short_kernel (rc_tile_short.cuh) in both
+    directions -- 16-byte vectors when extents, strides and pointers allow, element by element otherwise; unpacked
+    (sliced) short rows fall back to the rectangular / square tile.  All bit-exact."""
     rng = np.random.default_rng(seed_of(("strip", np.dtype(dtype).name)))
-    for k in (2, 3, 5, 8, 17, 31, 64):
-        for n in (1024, 5003):
-            a = rng.integers(0, 120, n * k).astype(dtype)
-            # short Y: source rows of k elements packed -> k long output rows
-            t = rt.Tensor(upload(dev, a), rt.Layout((k, n), (1, k))).to_contig(rt.ROW_MAJOR)
-            assert np.array_equal(t.to_numpy(), a.reshape(n, k).T), (dtype, k, n, "short y")
-            # short X: k long source rows -> output rows of k elements packed
-            t = rt.Tensor(upload(dev, a), rt.Layout((n, k), (1, n))).to_contig(rt.ROW_MAJOR)
-            assert np.array_equal(t.to_numpy(), a.reshape(k, n).T), (dtype, k, n, "short x")
-    # batched, and a sliced source whose short rows are NOT packed
+    for k in (2, 3, 4, 5, 8, 12, 17, 31, 32, 33, 48, 64, 65):
+        for n in (128, 130, 1024, 4112, 5003):
+            a = rng.integers(0, 120, n * k + 3).astype(dtype)
+            for off in (0, 1):  # off = 1: base pointer not 16-byte aligned -> scalar variant
+                # short Y: source rows of k elements packed -> k long output rows
+                t = rt.Tensor(upload(dev, a), rt.Layout((k, n), (1, k), off)).to_contig(rt.ROW_MAJOR)
+                assert np.array_equal(t.to_numpy(), a[off:off + n * k].reshape(n, k).T), (dtype, k, n, off, "short y")
+                # short X: k long source rows -> output rows of k elements packed
+                t = rt.Tensor(upload(dev, a), rt.Layout((n, k), (1, n), off)).to_contig(rt.ROW_MAJOR)
+                assert np.array_equal(t.to_numpy(), a[off:off + n * k].reshape(k, n).T), (dtype, k, n, off, "short x")
+    # batched (both directions), a pitched rows side, and a sliced source whose short rows are NOT packed
     a = rng.integers(0, 120, 3 * 4000 * 6).astype(dtype)
     t = rt.Tensor(upload(dev, a), rt.Layout((3, 6, 4000), (24000, 1, 6))).to_contig(rt.ROW_MAJOR)
     assert np.array_equal(t.to_numpy(), a.reshape(3, 4000, 6).transpose(0, 2, 1))
+    t = rt.Tensor(upload(dev, a), rt.Layout((3, 4000, 6), (24000, 1, 4000))).to_contig(rt.ROW_MAJOR)
+    assert np.array_equal(t.to_numpy(), a.reshape(3, 6, 4000).transpose(0, 2, 1))
+    t = rt.Tensor(upload(dev, a), rt.Layout((2048, 6), (1, 4000), 16)).to_contig(rt.ROW_MAJOR)  # k rows at pitch 4000
+    assert np.array_equal(t.to_numpy(), a[:24000].reshape(6, 4000)[:, 16:2064].T)
     t = rt.Tensor(upload(dev, a), rt.Layout((5, 4000), (1, 6), 1)).to_contig(rt.ROW_MAJOR)
     assert np.array_equal(t.to_numpy(), a[:24000].reshape(4000, 6)[:, 1:6].T)
+    # de-interleave INTO a pitched destination: k output rows of a wider array
+    src = rng.integers(0, 120, 2048 * 8).astype(dtype)
+    raw = upload(dev, np.zeros(8 * 2304, dtype=dtype))
+    dev.assign(raw, rt.Layout((8, 2048), (2304, 1), 128), upload(dev, src), rt.Layout((8, 2048), (1, 8)))
+    want = np.zeros((8, 2304), dtype=dtype)
+    want[:, 128:2176] = src.reshape(2048, 8).T
+    assert np.array_equal(dev.to_cpu_vec(raw).reshape(8, 2304), want)
