@@ -28,14 +28,29 @@ def name_of(dt) -> str:
     return NAME_OF[np.dtype(dt)]
 
 
+EXT_NAMES = ["f16", "bf16", "c32", "c64"]
+NP_EXT = {"f16": np.float16, "c32": np.complex64, "c64": np.complex128}  # bf16: ml_dtypes.bfloat16 where installed
+
+
 def promote(a: str, b: str) -> str:
     """<a as DTypePromoteAPI<b>>::Res"""
     if a == b:
         return a                                    # promotion.rs:41-55
     if a == "bool":
-        return b                                    # :123-141
+        return b                                    # :123-141 (every T incl. f16 / bf16 / c32 / c64: :195-200)
     if b == "bool":
         return a                                    # :143-157
+    if a in EXT_NAMES or b in EXT_NAMES:
+        ca, cb = a in ("c32", "c64"), b in ("c32", "c64")
+        if ca and cb:
+            return "c64"                            # c32 x c64 (:516-545)
+        if (ca or cb) and a not in ("f16", "bf16") and b not in ("f16", "bf16"):
+            c, p = (a, b) if ca else (b, a)
+            if c == "c64":
+                return "c64"                        # Complex<f64> x any primitive (:412-423, :493-505)
+            # Complex<f32> keeps f32 components for what f32 holds exactly (:406-410), else widens (:425-431)
+            return "c32" if p in ("i8", "i16", "u8", "u16", "f32") else "c64"
+        raise TypeError(f"DTypePromoteAPI<{b}> is not implemented for {a}")  # the half types pair with bool only
     fa, fb = a[0] == "f", b[0] == "f"
     if fa and fb:
         return "f64"                                # f32 x f64 (:266, :275)
@@ -57,8 +72,8 @@ def promote(a: str, b: str) -> str:
 
 
 def into_float(t: str) -> str:
-    if t in ("f32", "f64"):
-        return t
+    if t in ("f32", "f64") or t in EXT_NAMES:
+        return t                                    # promotion.rs:85-101
     if t == "bool":
         raise TypeError("DTypeIntoFloatAPI is not implemented for bool")
     return "f64"
@@ -82,6 +97,8 @@ def pow_kind(ta: str, tb: str) -> str:
 def op_types(op: str, ta: str, tb: str):
     """(compute type both operands are brought to, output type)"""
     if op == "pow":
+        if ta == tb and ta in EXT_NAMES:
+            return ta, ta                           # num_traits::Float::powf / Complex::powc of one type
         pow_kind(ta, tb)
         return ta, ta
     r = promote(ta, tb)

@@ -38,10 +38,20 @@ rc_dtype unsigned_of_bits(int bits) { return bits <= 8 ? RC_U8 : bits <= 16 ? RC
 
 rc_dtype promote(rc_dtype a, rc_dtype b) {
     if (a == b) return a;
-    RC_CHECK(!dtype_is_extended(a) && !dtype_is_extended(b), RC_ERR_UNIMPLEMENTED,
-             "promotion between half / complex and other element types is not implemented");
-    if (a == RC_BOOL) return b;  // bool x T -> T (promotion.rs:123-181)
+    if (a == RC_BOOL) return b;  // bool x T -> T (promotion.rs:123-181; f16 / bf16 / c32 / c64: :195-200)
     if (b == RC_BOOL) return a;
+    if (dtype_is_extended(a) || dtype_is_extended(b)) {
+        const bool ca = dtype_is_complex(a), cb = dtype_is_complex(b);
+        if (ca && cb) return RC_C64;  // c32 x c64 (promotion.rs:516-545)
+        if ((ca || cb) && !dtype_is_half(a) && !dtype_is_half(b)) {
+            const rc_dtype c = ca ? a : b, p = ca ? b : a;
+            if (c == RC_C64) return RC_C64;  // Complex<f64> x primitive (:412-423, :493-505)
+            // Complex<f32> keeps f32 components for the primitives f32 holds exactly (:406-410), else c64 (:425-431)
+            return (p == RC_I8 || p == RC_I16 || p == RC_U8 || p == RC_U16 || p == RC_F32) ? RC_C32 : RC_C64;
+        }
+        raise(RC_ERR_UNIMPLEMENTED, std::string("DTypePromoteAPI<") + dtype_name(b) + "> is not implemented for " + dtype_name(a) +
+                                        " (the half types pair with themselves and bool only, as in the reference)");
+    }
     const bool fa = dtype_is_float(a), fb = dtype_is_float(b);
     if (fa && fb) return RC_F64;  // f32 x f64
     if (fa || fb) {
@@ -61,7 +71,7 @@ rc_dtype promote(rc_dtype a, rc_dtype b) {
 }
 
 rc_dtype into_float(rc_dtype t) {  // DTypeIntoFloatAPI (promotion.rs:62-118): integers -> f64
-    if (t == RC_F32 || t == RC_F64) return t;
+    if (t == RC_F32 || t == RC_F64 || dtype_is_extended(t)) return t;  // promotion.rs:85-101
     RC_CHECK(t != RC_BOOL, RC_ERR_UNIMPLEMENTED, "bool has no float type (DTypeIntoFloatAPI is not implemented for bool)");
     return RC_F64;
 }
@@ -87,12 +97,13 @@ PowKind pow_kind(rc_dtype ta, rc_dtype tb) {
 // compute type K (both operands are brought to it) and output type of `op` for operand types (ta, tb)
 void op_types(rc_binop op, rc_dtype ta, rc_dtype tb, rc_dtype *k, rc_dtype *out) {
     if (dtype_is_extended(ta) || dtype_is_extended(tb)) {
-        // half / complex operands: same type on both sides (cast first otherwise); the library's promotion table covers the
-        // Rust primitives, as impl_promotion_asable! does
-        RC_CHECK(ta == tb, RC_ERR_UNIMPLEMENTED,
-                 std::string("mixed operand types with ") + dtype_name(dtype_is_extended(ta) ? ta : tb) + ": cast one operand first");
-        *k = ta;
-        *out = is_cmp_op(op) ? RC_BOOL : ta;
+        // half / complex operands: both are brought to promote(ta, tb) (bool x T, complex x primitive, c32 x c64 -- the rows
+        // of the reference's table; anything else raises), then the one-type kernel of that dtype runs
+        if (op == RC_POW && ta != tb)
+            raise(RC_ERR_UNIMPLEMENTED, std::string("pow is not implemented for ") + dtype_name(ta) + " ^ " + dtype_name(tb));
+        const rc_dtype r = promote(ta, tb);
+        *k = r;
+        *out = is_cmp_op(op) ? RC_BOOL : r;
         return;
     }
     if (op == RC_POW) {

@@ -94,6 +94,39 @@ void run_cast(rc_device *dev, rc_dtype tc, rc_dtype ta, const CanonEw &c, const 
     }
     if (dtype_is_extended(tc) || dtype_is_extended(ta)) {
         if (run_cast_ext(dev, tc, ta, c, args)) return;
+        // no direct kernel: stage through the real type the conversion is defined by.  primitive -> Complex<R> is
+        // `Complex::new(self as R, 0)` (DTypeCastAPI, promotion.rs:453-458); integer <-> half goes through f64 / f32 as
+        // half::f16::from_f64(v as f64) / (h.to_f32() as int) would.  One extra pass over a compact temporary.
+        rc_dtype via = RC_BOOL;
+        if (dtype_is_complex(tc) && !dtype_is_extended(ta)) via = tc == RC_C32 ? RC_F32 : RC_F64;
+        else if (dtype_is_half(tc) && !dtype_is_extended(ta)) via = RC_F64;
+        else if (dtype_is_half(ta) && !dtype_is_extended(tc)) via = RC_F32;
+        if (via != RC_BOOL) {
+            CanonEw c1 = c, c2 = c;  // slot 0 = output, slot 1 = source; the temporary is contiguous over the canonical shape
+            int64_t n = 1;
+            for (int i = 0; i < c.ndim; ++i) {
+                c1.stride[0][i] = n;
+                c2.stride[1][i] = n;
+                n *= c.shape[i];
+            }
+            c1.base[0] = 0;
+            c2.base[1] = 0;
+            void *tmp = nullptr;
+            cudaError_t e = cudaMallocAsync(&tmp, (size_t)n * dtype_size(via), dev->stream);
+            if (e != cudaSuccess) raise(RC_ERR_MEMORY, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+            try {
+                EwArgs a1 = args, a2 = args;
+                a1.c = tmp;
+                a2.a = tmp;
+                run_cast(dev, via, ta, c1, a1);
+                run_cast(dev, tc, via, c2, a2);
+            } catch (...) {
+                cudaFreeAsync(tmp, dev->stream);
+                throw;
+            }
+            cudaFreeAsync(tmp, dev->stream);
+            return;
+        }
         raise(RC_ERR_UNIMPLEMENTED, std::string("cast ") + dtype_name(ta) + " -> " + dtype_name(tc) + " is not implemented");
     }
     switch (tc) {

@@ -32,10 +32,37 @@ for t in PRIMS + ["bool"]:
     table[f"{t},{t}"] = t
 assert len(table) == 121, len(table)
 into_float = {t: ("f64" if t[0] in "iu" else t) for t in PRIMS}  # DTypeIntoFloatAPI: promotion.rs:62-118
+
+# ---- half / complex rows of the same file: bool x T (:195-200), complex x primitive (:368-431), primitive x complex
+# (:435-512), c32 x c64 (:516-545); no other half rule exists (f16 x f32 is NOT in the reference's table) ----
+EXT = {"half::f16": "f16", "half::bf16": "bf16", "c32": "c32", "c64": "c64"}
+CPLX = {"f32": "c32", "f64": "c64"}
+ext = {}
+for t in re.findall(r"impl_promotion_bool_T!\(([\w:]+)\);", src):
+    if t in EXT:
+        ext[f"bool,{EXT[t]}"] = EXT[t]
+        ext[f"{EXT[t]},bool"] = EXT[t]
+for kind, tc, tp, res in re.findall(r"impl_promotion_complex_primitive_(cast_self|no_cast_self)!\((\w+), (\w+), \w+, \w+, (\w+)\);", src):
+    p = ALIAS.get(tp, tp)
+    prev = ext.setdefault(f"{CPLX[tc]},{p}", CPLX[res])
+    assert prev == CPLX[res], (tc, tp, res)
+for kind, tc, tp, res in re.findall(r"impl_promotion_primitive_complex_(cast_other|nocast_other)!\((\w+), (\w+), \w+, \w+, (\w+)\);", src):
+    p = ALIAS.get(tp, tp)
+    prev = ext.setdefault(f"{p},{CPLX[tc]}", CPLX[res])
+    assert prev == CPLX[res], (tc, tp, res)
+assert "impl DTypePromoteAPI<c32> for c64" in src and "impl DTypePromoteAPI<c64> for c32" in src
+ext["c32,c64"] = ext["c64,c32"] = "c64"
+for t in EXT.values():
+    ext[f"{t},{t}"] = t
+for c in ("c32", "c64"):  # every primitive pairs with both complex types, in both orders
+    for t in PRIMS:
+        assert f"{c},{t}" in ext and f"{t},{c}" in ext, (c, t)
+into_float_ext = {t: t for t in EXT.values()}  # :85-101
 out = {"source": "rstsr-dtype-traits/src/promotion.rs (RESTGroup/rstsr v0.7.10): impl_promotion_asable!, "
                  "impl_promotion_bool_T!, impl<T> DTypePromoteAPI<T> for T; isize = i64, usize = u64",
-       "promote": dict(sorted(table.items())), "into_float": into_float}
+       "promote": dict(sorted(table.items())), "into_float": into_float,
+       "promote_ext": dict(sorted(ext.items())), "into_float_ext": into_float_ext}
 path = os.path.join(ROOT, "tests", "golden", "promotion_table.json")
 with open(path, "w") as f:
     json.dump(out, f, indent=1)
-print(path, len(table))
+print(path, len(table), len(ext))
