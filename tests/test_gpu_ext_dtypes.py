@@ -107,11 +107,17 @@ def test_casts(dev):
     assert e.value.kind == "UnImplemented"
 
 
+def _complex_of(re, im, dt):
+    out = np.empty(np.broadcast(re, im).shape, dtype=dt)  # componentwise: `re + 1j * im` would lose the sign of a zero
+    out.real, out.imag = re, im
+    return out
+
+
 def _cmul(a, b):
     rdt = a.real.dtype
     re = (a.real * b.real).astype(rdt) - (a.imag * b.imag).astype(rdt)
     im = (a.real * b.imag).astype(rdt) + (a.imag * b.real).astype(rdt)
-    return (re + 1j * im).astype(a.dtype)
+    return _complex_of(re, im, a.dtype)
 
 
 def _cdiv(a, b):
@@ -119,7 +125,7 @@ def _cdiv(a, b):
     n = (b.real * b.real).astype(rdt) + (b.imag * b.imag).astype(rdt)
     re = ((a.real * b.real).astype(rdt) + (a.imag * b.imag).astype(rdt)) / n
     im = ((a.imag * b.real).astype(rdt) - (a.real * b.imag).astype(rdt)) / n
-    return (re.astype(rdt) + 1j * im.astype(rdt)).astype(a.dtype)
+    return _complex_of(re.astype(rdt), im.astype(rdt), a.dtype)
 
 
 @pytest.mark.parametrize("dt", ALL, ids=_name)
@@ -273,3 +279,54 @@ def test_var_std_l2_and_arg_reductions(dev, dt):
         with pytest.raises(rt.RstsrCudaError) as e:
             t.argmax_all()
         assert e.value.kind == "UnImplemented"
+
+
+def test_promotion_with_complex_and_half_operands(dev):
+    """Mixed operand types through the reference's table (promotion.rs:195-200, :368-545): both operands are brought to
+    promote(ta, tb) -- primitive -> Complex<R> is (v as R, 0) -- and the one-type kernel runs: bit-exact against the same
+    two steps in NumPy."""
+    rng = np.random.default_rng(seed_of("extpromote"))
+    n = 3000
+    z32, z64 = _data(rng, n, np.complex64), _data(rng, n, np.complex128)
+    prim = {np.float32: rng.standard_normal(n).astype(np.float32), np.float64: rng.standard_normal(n),
+            np.int8: rng.integers(-100, 100, n).astype(np.int8), np.uint16: rng.integers(1, 60000, n).astype(np.uint16),
+            np.int32: rng.integers(-10**6, 10**6, n).astype(np.int32), np.int64: rng.integers(-10**12, 10**12, n),
+            np.uint64: rng.integers(1, 2**63, n).astype(np.uint64), np.bool_: rng.integers(0, 2, n).astype(np.bool_)}
+    up = lambda a: rt.asarray(a, dev)
+    for zdt, z in ((np.complex64, z32), (np.complex128, z64)):
+        for pdt, p in prim.items():
+            k = rt.DeviceCuda.promote_types(zdt, pdt)
+            small = np.dtype(pdt).kind == "b" or np.dtype(pdt) in (np.dtype(np.int8), np.dtype(np.uint16), np.dtype(np.float32))
+            assert k == np.dtype(zdt if (np.dtype(zdt) == np.complex128 or small) else np.complex128), (zdt, pdt)
+            rdt = np.float32 if k == np.complex64 else np.float64
+            zk, pk = z.astype(k), _complex_of(p.astype(rdt), np.zeros(n, rdt), k)
+            got = up(z) + up(p)
+            assert got.dtype == k and _same_bits(got.to_numpy(), zk + pk), (zdt, pdt, "add")
+            got = up(p) - up(z)
+            assert got.dtype == k and _same_bits(got.to_numpy(), pk - zk), (zdt, pdt, "sub")
+            assert _same_bits((up(z) * up(p)).to_numpy(), _cmul(zk, pk)), (zdt, pdt, "mul")
+            assert np.array_equal(up(z).binary("ne", up(p)).to_numpy(), zk != pk)
+    assert _same_bits((up(z32) / up(z64)).to_numpy(), _cdiv(z32.astype(np.complex128), z64))
+    # broadcast operand and a transposed view on the promoted side
+    col = prim[np.int32][:50]
+    m = z32[:50 * 60].reshape(50, 60)
+    got = rt.asarray(m.reshape(-1), dev).reshape([50, 60]).transpose([1, 0]) + up(col)
+    assert got.dtype == np.complex128 and _same_bits(got.to_numpy(), m.T.astype(np.complex128) + col.astype(np.float64))
+    for hdt in HALF:  # bool x half -> half; half x anything else is not in the reference's table
+        h, b = _data(rng, n, hdt), prim[np.bool_]
+        got = up(h) * up(b)
+        assert got.dtype == np.dtype(hdt) and _same_bits(got.to_numpy(), (h.astype(np.float32) * b.astype(np.float32)).astype(hdt))
+        with pytest.raises(rt.RstsrCudaError) as e:
+            up(h) + up(prim[np.float32])
+        assert e.value.kind == "UnImplemented"
+    # staged casts: primitive -> complex (v as R, 0), integer <-> half through f64 / f32
+    for pdt, p in prim.items():
+        for zdt, rdt in ((np.complex64, np.float32), (np.complex128, np.float64)):
+            got = up(p).astype(zdt).to_numpy()
+            assert _same_bits(got.real.copy(), p.astype(rdt)) and not got.imag.any(), (pdt, zdt)
+    i = rng.integers(-70000, 70000, n).astype(np.int32)
+    with np.errstate(over="ignore"):
+        want = i.astype(np.float64).astype(np.float16)
+    assert _same_bits(up(i).astype(np.float16).to_numpy(), want)
+    h = (rng.standard_normal(n) * 300).astype(np.float16)
+    assert np.array_equal(up(h).astype(np.int32).to_numpy(), h.astype(np.float32).astype(np.int32))

@@ -29,6 +29,49 @@ def test_product_promotion_matches_reference_table():
         assert PR.name_of(got) == want, key
 
 
+def _np_ext(name):
+    if name == "bf16":
+        return rt.bfloat16
+    return PR.NP_EXT.get(name) or PR.NP[name]
+
+
+def test_half_and_complex_rows_of_the_reference_table():
+    """bool x T, complex x primitive, primitive x complex, c32 x c64 (promotion.rs:195-200, :368-545): oracle and product
+    against the fixture generated from the reference's macro lines; every other pair with a half type is an error in
+    both, as it is a missing impl in the reference."""
+    ext = GOLD["promote_ext"]
+    assert len(ext) == 54
+    names = PR.NAMES + PR.EXT_NAMES
+    for a in names:
+        for b in names:
+            if a not in PR.EXT_NAMES and b not in PR.EXT_NAMES:
+                continue
+            key = f"{a},{b}"
+            usable = not ("bf16" in (a, b) and rt.bfloat16 is None)
+            if key in ext:
+                assert PR.promote(a, b) == ext[key], key
+                if usable:
+                    got = rt.DeviceCuda.promote_types(_np_ext(a), _np_ext(b))
+                    assert got == np.dtype(_np_ext(ext[key])), key
+            else:
+                with pytest.raises(TypeError):
+                    PR.promote(a, b)
+                if usable:
+                    with pytest.raises(rt.RstsrCudaError) as e:
+                        rt.DeviceCuda.promote_types(_np_ext(a), _np_ext(b))
+                    assert e.value.kind == "UnImplemented", key
+    for t, want in GOLD["into_float_ext"].items():
+        assert PR.into_float(t) == want
+    # TOut of the op classes on a promoted complex pair
+    D = rt.DeviceCuda
+    assert D.binop_out_dtype_ex("add", np.int32, np.complex64) == np.dtype(np.complex128)
+    assert D.binop_out_dtype_ex("mul", np.complex64, np.uint16) == np.dtype(np.complex64)
+    assert D.binop_out_dtype_ex("eq", np.float64, np.complex64) == np.dtype(np.bool_)
+    assert D.binop_out_dtype_ex("div", np.bool_, np.float16) == np.dtype(np.float16)
+    with pytest.raises(rt.RstsrCudaError):
+        D.binop_out_dtype_ex("pow", np.complex64, np.float32)
+
+
 OPS = ["add", "sub", "mul", "div", "maximum", "minimum", "floor_divide", "atan2", "copysign", "hypot", "nextafter",
        "logaddexp", "eq", "ne", "lt", "le", "gt", "ge", "pow"]
 
