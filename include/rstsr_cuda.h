@@ -73,7 +73,9 @@ typedef enum rc_dtype {
     /* round 2: half and complex element types (half::f16, half::bf16, num::Complex<f32>, num::Complex<f64>).
      * Arithmetic on the half types is f32 compute + ONE rounding, as the `half` crate does; complex mul / div use the
      * textbook formulas of num-complex.  Covered: storage, copy / to_contig / gather (raw words), fill, casts
-     * half <-> f32 / f64 / bool and real -> complex, c32 <-> c64; + - * / neg, comparisons (== != only for complex),
+     * half <-> f32 / f64 / bool / integers (through f64 / f32) and every primitive -> complex `(v as R, 0)`, c32 <-> c64;
+     * operand promotion as in the reference's table (bool x T, complex x primitive, c32 x c64: promotion.rs:195-200,
+     * :368-545; a half type pairs with itself and bool only, as there); + - * / neg, comparisons (== != only for complex),
      * maximum / minimum and the float math functions for half; abs / real / imag (real output), conj, square, exp, log,
      * sqrt, sin, cos, sinh, cosh, tanh, reciprocal for complex; reductions sum / prod / mean / var / std / l2_norm (all
      * four; var / std / l2_norm of complex are real), max / min / argmin / argmax / count_nonzero (half).
@@ -353,7 +355,8 @@ int rc_binop_out_dtype(rc_binop op, rc_dtype dtype, rc_dtype *out);
  * (rstsr-core/src/operators/ops/op_ternary_common.rs:22-57; impls
  * rstsr-core/src/feature_rayon/auto_impl/op_ternary_common.rs:6-120):
  *   R = DTypePromoteAPI<TB>::Res of TA   (NumPy's table, rstsr-dtype-traits/src/promotion.rs:186-300:
- *                                          i32 x f32 -> f64, i8 x u8 -> i16, i64 x u64 -> f64, bool x T -> T ...)
+ *                                          i32 x f32 -> f64, i8 x u8 -> i16, i64 x u64 -> f64, bool x T -> T ...;
+ *                                          :368-545: c32 x i8/i16/u8/u16/f32 -> c32, c32 x wider -> c64, c64 x any -> c64)
  *   atan2 copysign hypot nextafter logaddexp : both operands -> R -> DTypeIntoFloatAPI (ints -> f64), TOut = that float
  *   maximum minimum floor_divide             : both -> R, TOut = R
  *   == != < <= > >=                          : both -> R, TOut = bool
