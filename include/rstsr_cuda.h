@@ -365,9 +365,10 @@ int rc_binop_out_dtype(rc_binop op, rc_dtype dtype, rc_dtype *out);
  *   + - * / % | & ^ << >>                    : both -> R, TOut = R (the reference requires TA: Op<TB>; its tensor layer
  *                                              promotes first)
  * `tc` must be rc_binop_out_dtype_ex(op, ta, tb), else RC_ERR_INVALID_VALUE.  ta == tb runs the single fused kernel
- * of rc_op_mutc_refa_refb; otherwise the operand(s) whose type differs from the compute type are cast first
- * (element-exact `as` casts, broadcast axes kept compact), then the same kernel runs: results are bit-identical to
- * promote_pair + into_float + f per element.
+ * of rc_op_mutc_refa_refb; + - * / on f32 / i32 / i64 with f64 and i32 with i64 widen in registers inside one kernel;
+ * otherwise the operand(s) whose type differs from the compute type are cast first (element-exact `as` casts,
+ * broadcast axes kept compact), then the same kernel runs.  All three are bit-identical to promote_pair +
+ * into_float + f per element.
  * ---------------------------------------------------------------------------------------- */
 int rc_dtype_promote(rc_dtype ta, rc_dtype tb, rc_dtype *out);
 int rc_binop_out_dtype_ex(rc_binop op, rc_dtype ta, rc_dtype tb, rc_dtype *out);

@@ -268,6 +268,15 @@ int rc_op_mutc_refa_refb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, c
             return;
         }
         if (ta == k && tb == k) { status(rc_op_mutc_refa_refb(dev, op, k, c, lc, a, la_, b, lb_)); return; }
+        {   // common pairs: the widening cast happens in registers (rc_ew_mixed.cu), one pass over memory
+            Layout lcc = from_c(lc), la = from_c(la_), lb = from_c(lb_);
+            CanonEw cn = canon_elementwise({&lcc, &la, &lb}, false, true);
+            if (cn.empty) return;
+            RC_CHECK(c && a && b, RC_ERR_INVALID_VALUE, "null pointer");
+            EwArgs args;
+            args.c = c; args.a = a; args.b = b;
+            if (run_binary_promoted(dev, op, k, ta, tb, cn, args)) return;
+        }
         Operand oa, ob;
         prepare(dev, k, ta, a, from_c(la_), &oa);
         prepare(dev, k, tb, b, from_c(lb_), &ob);
@@ -298,6 +307,15 @@ int rc_op_mutc_refa_numb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, c
             return;
         }
         cast_host_scalar(k, tb, b_host, sb);
+        if (ta != k) {
+            Layout lcc = from_c(lc), la = from_c(la_);
+            CanonEw cn = canon_elementwise({&lcc, &la}, false, true);
+            if (cn.empty) return;
+            RC_CHECK(c && a, RC_ERR_INVALID_VALUE, "null pointer");
+            EwArgs args;
+            args.c = c; args.a = a; args.b_const = true; args.b_host = sb;
+            if (run_binary_promoted(dev, op, k, ta, k, cn, args)) return;
+        }
         Operand oa;
         prepare(dev, k, ta, a, from_c(la_), &oa);
         rc_layout cla;
@@ -328,6 +346,15 @@ int rc_op_mutc_numa_refb_ex(rc_device *dev, rc_binop op, rc_dtype tc, void *c, c
             return;
         }
         cast_host_scalar(k, ta, a_host, sa);
+        if (tb != k) {
+            Layout lcc = from_c(lc), lb = from_c(lb_);
+            CanonEw cn = canon_elementwise({&lcc, &lb}, false, true);
+            if (cn.empty) return;
+            RC_CHECK(c && b, RC_ERR_INVALID_VALUE, "null pointer");
+            EwArgs args;
+            args.c = c; args.a_const = true; args.a_host = sa; args.b = b;
+            if (run_binary_promoted(dev, op, k, k, tb, cn, args)) return;
+        }
         Operand ob;
         prepare(dev, k, tb, b, from_c(lb_), &ob);
         rc_layout clb;

@@ -9,6 +9,8 @@ struct EwArgs;
 
 // c = a o b (arithmetic: rc_ew_arith.cu, bit ops: rc_ew_bit.cu, functions: rc_ew_func.cu, comparisons: rc_ew_cmp.cu)
 void run_binary_arith(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+// promote_pair fused into the kernel for the common mixed pairs (rc_ew_mixed.cu); false = no such kernel
+bool run_binary_promoted(rc_device *dev, rc_binop op, rc_dtype k, rc_dtype ta, rc_dtype tb, const CanonEw &c, const EwArgs &args);
 void run_binary_bit(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
 void run_binary_func(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
 void run_binary_cmp(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, const EwArgs &args);

@@ -279,3 +279,62 @@ def test_outer_ops_take_both_operand_orders(dev, dtype):
             assert np.array_equal(tu.binary("div", tv).to_numpy(), uu / v[None, :])
             assert np.array_equal(tv.binary("div", tu).to_numpy(), v[None, :] / uu)
             assert np.array_equal(tu.binary("lt", tv).to_numpy(), uu < v[None, :])
+
+
+FUSED_PAIRS = [(np.float32, np.float64), (np.int32, np.float64), (np.int64, np.float64), (np.int32, np.int64)]
+
+
+@pytest.mark.parametrize("pair", FUSED_PAIRS, ids=lambda p: f"{np.dtype(p[0]).name}-{np.dtype(p[1]).name}")
+def test_fused_promotion_pairs(dev, pair):
+    """+ - * / on the pairs whose widening cast is fused into the kernel (rc_ew_mixed.cu), in both operand orders and
+    through every kernel family -- 16/32-byte packs, rows with a broadcast operand, transposed operand (tile), short
+    transposed axis (rect tile), outer product, scalar operand on either side, odd sizes on the scalar path: bit-exact
+    against `a as K op b as K` (Rust's wrapping integer arithmetic for K = i64; / on integers only where b != 0)."""
+    tn, tw = pair
+    K = np.promote_types(tn, tw)
+    assert rt.DeviceCuda.promote_types(tn, tw) == K
+    rng = np.random.default_rng(seed_of(("fused", np.dtype(tn).name, np.dtype(tw).name)))
+
+    def data(n, dt):
+        if np.dtype(dt).kind == "f":
+            return (rng.standard_normal(n) * 100).astype(dt)
+        x = rng.integers(-2**20, 2**20, n).astype(dt)
+        x[x == 0] = 7
+        return x
+
+    ops = {"add": np.add, "sub": np.subtract, "mul": np.multiply}
+    if K.kind == "f":
+        ops["div"] = np.divide
+
+    def check(x, y, xa, ya, what):
+        for op, fn in ops.items():
+            z = x.binary(op, y)
+            assert z.dtype == K, (op, what)
+            want = fn(np.asarray(xa).astype(K), np.asarray(ya).astype(K))
+            assert np.array_equal(z.to_numpy(), want), (op, what, pair)
+
+    for first_narrow in (True, False):
+        ta, tb = (tn, tw) if first_narrow else (tw, tn)
+        # (1) flat packs + odd tail; (2) rows with a broadcast row; (3) transposed operand; (4) short transposed axis; (5) outer
+        a, b = data(256 * 1024 + 3, ta), data(256 * 1024 + 3, tb)
+        check(rt.asarray(a, dev), rt.asarray(b, dev), a, b, "flat")
+        a, b = data(384 * 1024, ta).reshape(384, 1024), data(1024, tb)
+        check(rt.asarray(a.reshape(-1), dev).reshape([384, 1024]), rt.asarray(b, dev), a, b, "rows")
+        a, b = data(512 * 640, ta).reshape(512, 640), data(640 * 512, tb).reshape(640, 512)
+        check(rt.asarray(a.reshape(-1), dev).reshape([512, 640]), rt.asarray(b.reshape(-1), dev).reshape([640, 512]).transpose([1, 0]),
+              a, b.T, "tile")
+        a, b = data(4096 * 6, ta).reshape(4096, 6), data(6 * 4096, tb).reshape(6, 4096)
+        check(rt.asarray(a.reshape(-1), dev).reshape([4096, 6]), rt.asarray(b.reshape(-1), dev).reshape([6, 4096]).transpose([1, 0]),
+              a, b.T, "rect")
+        a, b = data(700, ta), data(900, tb)
+        check(rt.asarray(a, dev).reshape([700, 1]), rt.asarray(b, dev).reshape([1, 900]), a.reshape(700, 1), b.reshape(1, 900), "outer")
+    # scalar operands through the C ABI entry points (the tensor-level mirror only mixes float scalars with int tensors)
+    a = data(5000, tn)
+    s = np.asarray(data(1, tw))[0]
+    la = rt.Layout((5000,), (1,))
+    for op, fn in ops.items():
+        out = dev.uninit_impl(K, 5000)
+        dev.op_mutc_refa_numb(op, out, la, upload(dev, a), la, s, b_dtype=np.dtype(tw))
+        assert np.array_equal(dev.to_cpu_vec(out), fn(a.astype(K), K.type(s))), (op, "numb")
+        dev.op_mutc_numa_refb(op, out, la, s, upload(dev, a), la, a_dtype=np.dtype(tw))
+        assert np.array_equal(dev.to_cpu_vec(out), fn(K.type(s), a.astype(K))), (op, "numa")
