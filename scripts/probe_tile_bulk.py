@@ -28,7 +28,7 @@ def run(name, shape, perm, dtype=torch.float64, iters=10):
     if dtype != torch.float64:
         src = src.to(dtype)
     dst = torch.empty_like(src)
-    npdt = {torch.float64: np.float64, torch.int64: np.int64}[dtype]
+    npdt = {torch.float64: np.float64, torch.int64: np.int64, torch.float32: np.float32}[dtype]
     rs, rd = dev.wrap(src.data_ptr(), n, npdt), dev.wrap(dst.data_ptr(), n, npdt)
     st = [int(np.prod(shape[i + 1:])) for i in range(len(shape))]
     lsrc = Layout(tuple(shape[p] for p in perm), tuple(st[p] for p in perm))
@@ -62,5 +62,8 @@ run("(512,512,2048) perm (1,2,0)", (512, 512, 2048), (1, 2, 0))
 run("4-D (32,64,512,512) perm (1,0,3,2)", (32, 64, 512, 512), (1, 0, 3, 2))
 run("small (1024,1024) transpose", (1024, 1024), (1, 0), iters=50)
 run("i64 (4096,8192) transpose", (4096, 8192), (1, 0), dtype=torch.int64)
+run("f32 2-D transpose (32768,16384)", (32768, 16384), (1, 0), dtype=torch.float32)
+run("f32 (1024,1024,1024) perm (2,0,1)", (1024, 1024, 1024), (2, 0, 1), dtype=torch.float32)
+run("f32 batched (128,2048,2048) perm (0,2,1)", (128, 2048, 2048), (0, 2, 1), dtype=torch.float32)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"probe_tile_bulk_{mode}.json"), "w"), indent=1)
