@@ -302,3 +302,33 @@ def test_short_axis_packed_transposes(dev, dtype):
     want = np.zeros((8, 2304), dtype=dtype)
     want[:, 128:2176] = src.reshape(2048, 8).T
     assert np.array_equal(dev.to_cpu_vec(raw).reshape(8, 2304), want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int16, np.uint8])
+def test_random_permutations_through_the_tile_kernels(dev, dtype):
+    """Seeded random 3- / 4-D permutations whose extents straddle the selection thresholds of the square, wide, word,
+    rectangular and short-axis tiles (short extents 2..70, long ones 100..700, sliced / flipped sources, both targets):
+    whichever kernel the launcher picks, the copy is bit-exact."""
+    rng = np.random.default_rng(seed_of(("randperm", np.dtype(dtype).name)))
+    for case in range(48):
+        nd = int(rng.integers(2, 5))
+        shape = [int(rng.choice([rng.integers(2, 71), rng.integers(100, 700)])) for _ in range(nd)]
+        while int(np.prod(shape)) > (1 << 22):
+            shape[int(np.argmax(shape))] //= 2
+        perm = [int(p) for p in rng.permutation(nd)]
+        a = rng.integers(0, 120, int(np.prod(shape))).astype(dtype)
+        view = a.reshape(shape).transpose(perm)
+        la = L.c_contig_layout(shape).transpose(perm)
+        if case % 3 == 1:      # a slice: offsets and pitches that break the vector / flat preconditions
+            ax = int(rng.integers(0, nd))
+            lo = int(rng.integers(0, 3))
+            la = la.narrow(ax, slice(lo, None))
+            view = view[(slice(None),) * ax + (slice(lo, None),)]
+        elif case % 3 == 2:    # a flipped axis
+            ax = int(rng.integers(0, nd))
+            la = la.narrow(ax, slice(None, None, -1))
+            view = view[(slice(None),) * ax + (slice(None, None, -1),)]
+        for target, order in ((rt.ROW_MAJOR, "C"), (rt.COL_MAJOR, "F")):
+            t = rt.Tensor(upload(dev, a), P(la)).to_contig(target)
+            got = t.to_numpy()
+            assert got.shape == view.shape and np.array_equal(got, view), (dtype, case, shape, perm, order)
