@@ -76,9 +76,12 @@ typedef enum rc_dtype {
      * half <-> f32 / f64 / bool / integers (through f64 / f32) and every primitive -> complex `(v as R, 0)`, c32 <-> c64;
      * operand promotion as in the reference's table (bool x T, complex x primitive, c32 x c64: promotion.rs:195-200,
      * :368-545; a half type pairs with itself and bool only, as there); + - * / neg, comparisons (== != only for complex),
-     * maximum / minimum and the float math functions for half; abs / real / imag (real output), conj, square, exp, log,
-     * sqrt, sin, cos, sinh, cosh, tanh, reciprocal for complex; reductions sum / prod / mean / var / std / l2_norm (all
-     * four; var / std / l2_norm of complex are real), max / min / argmin / argmax / count_nonzero (half).
+     * maximum / minimum and the float math functions for half; abs / real / imag (real output), conj, square, reciprocal and
+     * every ComplexFloat function of the reference for complex (exp log log2 log10 sqrt sin cos tan asin acos atan sinh
+     * cosh tanh asinh acosh atanh; is_nan / is_infinite / is_finite); reductions sum / prod / mean / var / std / l2_norm
+     * (all four; var / std / l2_norm of complex are real), max / min / argmin / argmax / count_nonzero (half); vecdot
+     * (sum conj(a) b), allclose_all; linspace (all four, in the type's own arithmetic), arange (half: the reference's
+     * serial recurrence), tril / triu.
      * Anything else on these types is RC_ERR_UNIMPLEMENTED. */
     RC_F16 = 11,
     RC_BF16 = 12,

@@ -7,6 +7,7 @@
 
 #include "rc_kernel_common.cuh"
 #include "rc_layout.hpp"
+#include "rc_types.cuh"
 
 namespace rc {
 namespace {
@@ -29,6 +30,52 @@ __global__ void linspace_kernel(T *out, int64_t n, T start, T step) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = start + (T)i * step;
 }
+
+// the same for the half / complex element types, in THEIR arithmetic (half: every op through f32 and one rounding;
+// complex: the textbook product of rc_types.cuh).  T::from(i): NumCast of the half types goes through f32, of Complex<R>
+// to (R::from(i), 0).
+template <class T> __device__ __forceinline__ T from_index(int64_t i) {
+    if constexpr (is_half_t<T>::value) return T((float)i);
+    else return T((typename real_of<T>::type)i, (typename real_of<T>::type)0);
+}
+template <class T>
+__global__ void linspace_x_kernel(T *out, int64_t n, T start, T step) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = start + from_index<T>(i) * step;
+}
+template <class T> T host_from_count(int64_t v) {
+    if constexpr (is_half_t<T>::value) return T((float)v);
+    else return T((typename real_of<T>::type)v, (typename real_of<T>::type)0);
+}
+template <class T>
+void linspace_x(rc_device *dev, void *p, const void *start, const void *end, int64_t n, int endpoint) {
+    T s, e;
+    std::memcpy(&s, start, sizeof(T));
+    std::memcpy(&e, end, sizeof(T));
+    // step = (end - start) / T::from(n - 1 | n) in T (cpu_rayon/creation.rs:121-124); n == 1 returns [start]
+    const T step = (n == 1) ? host_from_count<T>(0) : (e - s) / host_from_count<T>(endpoint ? n - 1 : n);
+    const unsigned B = 256, grid = (unsigned)((n + B - 1) / B);
+    linspace_x_kernel<T><<<grid, B, 0, dev->stream>>>((T *)p, n, s, step);
+}
+
+// arange of the types that take the reference's generic fallback (arange_by_partial_ord_cpu_serial,
+// cpu_serial/creation.rs:7-19): `while current < end { push(current); current = current + step }` in the element type --
+// a sequential recurrence (half types round at every step), so it is evaluated on the host and uploaded.
+constexpr int64_t kMaxSerialArange = 1 << 24;
+template <class T, class Next>
+std::vector<T> arange_serial(T start, T end, Next next) {
+    std::vector<T> v;
+    T cur = start;
+    while (cur < end) {
+        RC_CHECK((int64_t)v.size() < kMaxSerialArange, RC_ERR_INVALID_VALUE,
+                 "arange of an 8- / 16-bit type does not terminate within 2^24 elements (step too small or wrapping)");
+        v.push_back(cur);
+        cur = next(cur);
+    }
+    return v;
+}
+
+struct alignas(16) W16 { uint64_t lo, hi; };  // a 16-byte element (c64) as raw words
 
 struct TriDesc {
     int ndim;
@@ -54,7 +101,7 @@ __global__ void __launch_bounds__(256) tri_kernel(const __grid_constant__ TriDes
         t = q;
     }
     const bool zero = d.lower ? (j > i + d.k) : (j < i + d.k);
-    if (zero) a[off] = (U)0;
+    if (zero) a[off] = U{};
 }
 
 template <class U>
@@ -79,7 +126,7 @@ int64_t host_as_i64(rc_dtype t, const void *p) {
         case RC_U64: { uint64_t v; std::memcpy(&v, p, 8); RC_CHECK(v <= (uint64_t)INT64_MAX, RC_ERR_INVALID_VALUE, "arange bound exceeds isize"); return (int64_t)v; }
         default: break;
     }
-    raise(RC_ERR_UNIMPLEMENTED, "arange is implemented for i32, i64, u32, u64, f32, f64");
+    raise(RC_ERR_UNIMPLEMENTED, "arange is not implemented for this dtype (complex numbers and bool have no ordering / step)");
 }
 
 void *dev_alloc(rc_device *dev, size_t nbytes) {
@@ -103,7 +150,41 @@ int rc_arange(rc_device *dev, rc_dtype t, const void *start, const void *end, co
         RC_CHECK(start && end && step && out_dev && n_out, RC_ERR_INVALID_VALUE, "null argument");
         int64_t n = 0;
         const unsigned B = 256;
-        if (dtype_is_float(t)) {
+        if (t == RC_I8 || t == RC_I16 || t == RC_U8 || t == RC_U16 || dtype_is_half(t)) {
+            // generic fallback of the reference: a serial recurrence in the element type
+            std::vector<unsigned char> bytes;
+            auto pack = [&](const auto &v) {
+                n = (int64_t)v.size();
+                bytes.resize(v.size() * sizeof(v[0]));
+                if (!v.empty()) std::memcpy(bytes.data(), v.data(), bytes.size());
+            };
+            auto ints = [&](auto zero) {
+                using T = decltype(zero);
+                T s, e, st;
+                std::memcpy(&s, start, sizeof(T)); std::memcpy(&e, end, sizeof(T)); std::memcpy(&st, step, sizeof(T));
+                pack(arange_serial<T>(s, e, [st](T c) { return (T)(c + st); }));  // wrapping, as release builds do
+            };
+            auto halves = [&](auto zero) {
+                using T = decltype(zero);
+                T s, e, st;
+                std::memcpy(&s, start, sizeof(T)); std::memcpy(&e, end, sizeof(T)); std::memcpy(&st, step, sizeof(T));
+                pack(arange_serial<T>(s, e, [st](T c) { return c + st; }));
+            };
+            switch (t) {
+                case RC_I8: ints(int8_t()); break;
+                case RC_I16: ints(int16_t()); break;
+                case RC_U8: ints(uint8_t()); break;
+                case RC_U16: ints(uint16_t()); break;
+                case RC_F16: halves(h16()); break;
+                default: halves(b16()); break;
+            }
+            void *p = dev_alloc(dev, bytes.size());
+            if (!bytes.empty()) {
+                RC_CUDA(cudaMemcpyAsync(p, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, dev->stream));
+                RC_CUDA(cudaStreamSynchronize(dev->stream));  // `bytes` is pageable and dies with this scope
+            }
+            *out_dev = p;
+        } else if (dtype_is_float(t)) {
             const double s = host_as_f64(t, start), e = host_as_f64(t, end), st = host_as_f64(t, step);
             RC_CHECK(st != 0.0, RC_ERR_INVALID_VALUE, "arange step must not be zero");  // auto_impl/creation.rs:81
             double cnt = std::ceil((e - s) / st);
@@ -151,12 +232,20 @@ int rc_linspace(rc_device *dev, rc_dtype t, const void *start, const void *end, 
         DeviceGuard g(dev);
         RC_CHECK(start && end && out_dev, RC_ERR_INVALID_VALUE, "null argument");
         RC_CHECK(n >= 0, RC_ERR_INVALID_VALUE, "negative length");
-        RC_CHECK(dtype_is_float(t), RC_ERR_UNIMPLEMENTED, "linspace requires a floating-point dtype");
+        RC_CHECK(dtype_is_float(t) || dtype_is_extended(t), RC_ERR_UNIMPLEMENTED,
+                 "linspace requires a floating-point or complex dtype (T: ComplexFloat)");
         void *p = dev_alloc(dev, (size_t)n * dtype_size(t));
         *out_dev = p;
         if (n == 0) return;
         const unsigned B = 256, grid = (unsigned)((n + B - 1) / B);
-        if (t == RC_F64) {
+        if (dtype_is_extended(t)) {
+            switch (t) {
+                case RC_F16: linspace_x<h16>(dev, p, start, end, n, endpoint); break;
+                case RC_BF16: linspace_x<b16>(dev, p, start, end, n, endpoint); break;
+                case RC_C32: linspace_x<c32>(dev, p, start, end, n, endpoint); break;
+                default: linspace_x<c64>(dev, p, start, end, n, endpoint); break;
+            }
+        } else if (t == RC_F64) {
             double s, e;
             std::memcpy(&s, start, 8);
             std::memcpy(&e, end, 8);
@@ -197,7 +286,8 @@ static int tri_impl(rc_device *dev, rc_dtype t, void *a, const rc_layout *l_, in
             case 1: tri_launch<uint8_t>(dev, d, p); break;
             case 2: tri_launch<uint16_t>(dev, d, p); break;
             case 4: tri_launch<uint32_t>(dev, d, p); break;
-            default: tri_launch<uint64_t>(dev, d, p); break;
+            case 8: tri_launch<uint64_t>(dev, d, p); break;
+            default: tri_launch<W16>(dev, d, p); break;
         }
     });
 }

@@ -43,6 +43,23 @@ RC_CPLX_MATH(FCCos, thrust::cos(z))
 RC_CPLX_MATH(FCSinh, thrust::sinh(z))
 RC_CPLX_MATH(FCCosh, thrust::cosh(z))
 RC_CPLX_MATH(FCTanh, thrust::tanh(z))
+RC_CPLX_MATH(FCTan, thrust::tan(z))
+RC_CPLX_MATH(FCAsin, thrust::asin(z))
+RC_CPLX_MATH(FCAcos, thrust::acos(z))
+RC_CPLX_MATH(FCAtan, thrust::atan(z))
+RC_CPLX_MATH(FCAsinh, thrust::asinh(z))
+RC_CPLX_MATH(FCAcosh, thrust::acosh(z))
+RC_CPLX_MATH(FCAtanh, thrust::atanh(z))
+// num-complex: log2 / log10 = ln(z) scaled by 1 / ln(base) on both components (Complex::log(base) via to_polar)
+RC_CPLX_MATH(FCLog2, thrust::log(z) / thrust::complex<R>((R)0.693147180559945309417232121458176568))
+RC_CPLX_MATH(FCLog10, thrust::log(z) / thrust::complex<R>((R)2.302585092994045684017991454684364208))
+// predicates (num-complex): is_nan = re or im NaN; is_infinite = not NaN and re or im infinite; is_finite = both finite
+template <class R> struct FCIsNan { using TA = cplx<R>; using TB = TA; using TO = uint8_t; static constexpr int NIN = 1;
+    RC_FN uint8_t apply(TA a) { return (a.re != a.re) || (a.im != a.im); } };
+template <class R> struct FCIsInf { using TA = cplx<R>; using TB = TA; using TO = uint8_t; static constexpr int NIN = 1;
+    RC_FN uint8_t apply(TA a) { return !((a.re != a.re) || (a.im != a.im)) && (isinf(a.re) || isinf(a.im)); } };
+template <class R> struct FCIsFinite { using TA = cplx<R>; using TB = TA; using TO = uint8_t; static constexpr int NIN = 1;
+    RC_FN uint8_t apply(TA a) { return isfinite(a.re) && isfinite(a.im); } };
 
 // ---------------- casts ----------------
 template <class TOut, class TIn> struct conv_t {

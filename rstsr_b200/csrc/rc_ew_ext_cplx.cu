@@ -37,7 +37,10 @@ bool run_unary_cplx(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, co
             RC_CPLX_UN(RC_ABS, FCAbs) RC_CPLX_UN(RC_REAL, FCReal) RC_CPLX_UN(RC_IMAG, FCImag) RC_CPLX_UN(RC_CONJ, FCConj)
             RC_CPLX_UN(RC_RECIPROCAL, FCRecip) RC_CPLX_UN(RC_EXP, FCExp) RC_CPLX_UN(RC_LOG, FCLog) RC_CPLX_UN(RC_SQRT, FCSqrt)
             RC_CPLX_UN(RC_SIN, FCSin) RC_CPLX_UN(RC_COS, FCCos) RC_CPLX_UN(RC_SINH, FCSinh) RC_CPLX_UN(RC_COSH, FCCosh)
-            RC_CPLX_UN(RC_TANH, FCTanh)
+            RC_CPLX_UN(RC_TANH, FCTanh) RC_CPLX_UN(RC_TAN, FCTan) RC_CPLX_UN(RC_ASIN, FCAsin) RC_CPLX_UN(RC_ACOS, FCAcos)
+            RC_CPLX_UN(RC_ATAN, FCAtan) RC_CPLX_UN(RC_ASINH, FCAsinh) RC_CPLX_UN(RC_ACOSH, FCAcosh) RC_CPLX_UN(RC_ATANH, FCAtanh)
+            RC_CPLX_UN(RC_LOG2, FCLog2) RC_CPLX_UN(RC_LOG10, FCLog10)
+            RC_CPLX_UN(RC_ISNAN, FCIsNan) RC_CPLX_UN(RC_ISINF, FCIsInf) RC_CPLX_UN(RC_ISFINITE, FCIsFinite)
             default: break;
         }
     }

@@ -58,9 +58,21 @@ void check_dev_ptr(const void *p, const char *name) {
     if (!p) raise(RC_ERR_INVALID_VALUE, std::string("null device pointer: ") + name);
 }
 
+}  // namespace
+// half / complex element types (rc_reduce_extx.cu)
+void run_vecdot_extx(rc_device *dev, rc_dtype t, const CanonRed &cr, const void *a, const void *b, void *c, int64_t n);
+void run_allclose_extx(rc_device *dev, rc_dtype t, const CanonRed &cr, const void *a, const void *b, void *out, int64_t n,
+                       double rtol, double atol, int equal_nan);
+namespace {
+
 template <template <class> class P>
 void dispatch(rc_device *dev, rc_dtype t, const CanonRed &cr, const void *a, const void *b, void *out, int64_t n,
               double fp0, double fp1, int ip0) {
+    if (dtype_is_extended(t)) {
+        if (std::is_same<P<float>, PDot<float>>::value) run_vecdot_extx(dev, t, cr, a, b, out, n);
+        else run_allclose_extx(dev, t, cr, a, b, out, n, fp0, fp1, ip0);
+        return;
+    }
     switch (t) {
         case RC_F64: reduce_typed<P<double>>(dev, cr, a, out, n, b, fp0, fp1, ip0); return;
         case RC_F32: reduce_typed<P<float>>(dev, cr, a, out, n, b, fp0, fp1, ip0); return;

@@ -85,7 +85,76 @@ void reduce_cplx(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, 
                                 "(ExtReal is not implemented for Complex)");
 }
 
+// ---- vecdot: sum conj(a) * b (cpu_serial/vecdot.rs:96-157; ExtNum::ext_conj is the identity on real types) ----
+template <class R> struct PCDot {
+    static constexpr bool BINARY = true;
+    using TI = cplx<R>; using S = cplx<R>; using TO = cplx<R>; using Second = PSum<cplx<R>>;
+    static __device__ __forceinline__ S init() { return cplx<R>((R)0, (R)0); }
+    static __device__ __forceinline__ S pre2(TI x, TI y, const RedDesc &) { return cplx<R>(x.re, -x.im) * y; }
+    static __device__ __forceinline__ S comb(S a, S b) { return a + b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
+};
+// half: the product is rounded to the element type as `x * y` is, accumulated in f32, ONE rounding of the sum
+template <class T> struct PHDot {
+    static constexpr bool BINARY = true;
+    using TI = T; using S = float; using TO = T; using Second = PState<PHDot<T>>;
+    static __device__ __forceinline__ S init() { return 0.0f; }
+    static __device__ __forceinline__ S pre2(T x, T y, const RedDesc &) { return (x * y).f(); }
+    static __device__ __forceinline__ S comb(S a, S b) { return a + b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return T(s); }
+};
+// ---- allclose_all: |a - b| <= atol + rtol * |b| with TE = f64 (rstsr-dtype-traits/src/isclose.rs:92-106); the difference
+// and |b| are formed in the element type (complex: Complex::norm = hypot) and then widened ----
+template <class T> struct PCloseX {
+    static constexpr bool BINARY = true;
+    using TI = T; using S = uint8_t; using TO = uint8_t; using Second = PLogic<true>;
+    static __device__ __forceinline__ S init() { return 1; }
+    static __device__ __forceinline__ S pre2(T a, T b, const RedDesc &d) {
+        double diff, abs_b;
+        bool both_nan;
+        if constexpr (is_cplx_t<T>::value) {
+            using R = typename real_of<T>::type;
+            const T df = a - b;
+            if constexpr (sizeof(R) == 4) { diff = (double)hypotf(df.re, df.im); abs_b = (double)hypotf(b.re, b.im); }
+            else { diff = hypot(df.re, df.im); abs_b = hypot(b.re, b.im); }
+            both_nan = (a.re != a.re || a.im != a.im) && (b.re != b.re || b.im != b.im);
+        } else {
+            const float df = (a - b).f(), fb = b.f();  // a - b rounded to the half type first
+            diff = (double)fabsf(df);
+            abs_b = (double)fabsf(fb);
+            both_nan = a.f() != a.f() && fb != fb;
+        }
+        const bool ok = diff <= d.fp1 + d.fp0 * abs_b || (d.ip0 && both_nan);
+        return ok ? 1 : 0;
+    }
+    static __device__ __forceinline__ S comb(S a, S b) { return a & b; }
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s; }
+};
+
 }  // namespace
+
+void run_vecdot_extx(rc_device *dev, rc_dtype t, const CanonRed &cr, const void *a, const void *b, void *c, int64_t n) {
+    switch (t) {
+        case RC_F16: reduce_typed<PHDot<h16>>(dev, cr, a, c, n, b, 0.0, 0.0, 0); return;
+        case RC_BF16: reduce_typed<PHDot<b16>>(dev, cr, a, c, n, b, 0.0, 0.0, 0); return;
+        case RC_C32: reduce_typed<PCDot<float>>(dev, cr, a, c, n, b, 0.0, 0.0, 0); return;
+        case RC_C64: reduce_typed<PCDot<double>>(dev, cr, a, c, n, b, 0.0, 0.0, 0); return;
+        default: break;
+    }
+    raise(RC_ERR_INVALID_VALUE, "not an extended dtype");
+}
+
+void run_allclose_extx(rc_device *dev, rc_dtype t, const CanonRed &cr, const void *a, const void *b, void *out, int64_t n,
+                       double rtol, double atol, int equal_nan) {
+    switch (t) {
+        case RC_F16: reduce_typed<PCloseX<h16>>(dev, cr, a, out, n, b, rtol, atol, equal_nan); return;
+        case RC_BF16: reduce_typed<PCloseX<b16>>(dev, cr, a, out, n, b, rtol, atol, equal_nan); return;
+        case RC_C32: reduce_typed<PCloseX<c32>>(dev, cr, a, out, n, b, rtol, atol, equal_nan); return;
+        case RC_C64: reduce_typed<PCloseX<c64>>(dev, cr, a, out, n, b, rtol, atol, equal_nan); return;
+        default: break;
+    }
+    raise(RC_ERR_INVALID_VALUE, "not an extended dtype");
+}
 
 void run_reduce_extx(rc_device *dev, rc_redop op, rc_dtype t, const CanonRed &cr, const void *a, void *out, int64_t n) {
     switch (t) {

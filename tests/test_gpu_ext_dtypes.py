@@ -330,3 +330,96 @@ def test_promotion_with_complex_and_half_operands(dev):
     assert _same_bits(up(i).astype(np.float16).to_numpy(), want)
     h = (rng.standard_normal(n) * 300).astype(np.float16)
     assert np.array_equal(up(h).astype(np.int32).to_numpy(), h.astype(np.float32).astype(np.int32))
+
+
+@pytest.mark.parametrize("dt", CPLX, ids=_name)
+def test_complex_inverse_functions_and_predicates(dev, dt):
+    """tan, the inverse trigonometric / hyperbolic functions, log2 / log10 and is_nan / is_infinite / is_finite of complex
+    numbers (ComplexFloat rows of auto_impl/op_binary_common.rs:10-35, :97-102).  libm-style: 1e-5 / 1e-12 relative
+    against NumPy's C99 functions (same principal branches as num-complex)."""
+    rng = np.random.default_rng(seed_of(("cinv", _name(dt))))
+    z = _data(rng, 4000, dt)
+    t = rt.asarray(z, dev)
+    tol = 2e-5 if np.dtype(dt) == np.complex64 else 1e-12
+    fns = {"tan": np.tan, "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan, "asinh": np.arcsinh, "acosh": np.arccosh,
+           "atanh": np.arctanh, "log2": np.log2, "log10": np.log10}
+    for op, fn in fns.items():
+        got = t.unary(op)
+        assert got.dtype == np.dtype(dt)
+        want = fn(z.astype(np.complex128))
+        err = np.abs(got.to_numpy().astype(np.complex128) - want) / np.maximum(np.abs(want), 1.0)
+        assert err.max() <= tol, (dt, op, err.max())
+    w = z.copy()
+    w[:6] = [complex(np.nan, 1), complex(1, np.nan), complex(np.inf, 0), complex(0, -np.inf), complex(np.inf, np.nan), 0]
+    tw = rt.asarray(w, dev)
+    nan = np.isnan(w.real) | np.isnan(w.imag)
+    inf = ~nan & (np.isinf(w.real) | np.isinf(w.imag))
+    assert np.array_equal(tw.unary("isnan").to_numpy(), nan)
+    assert np.array_equal(tw.unary("isinf").to_numpy(), inf)
+    assert np.array_equal(tw.unary("isfinite").to_numpy(), np.isfinite(w.real) & np.isfinite(w.imag))
+
+
+@pytest.mark.parametrize("dt", ALL, ids=_name)
+def test_vecdot_and_allclose(dev, dt):
+    """vecdot = sum conj(a) * b (cpu_serial/vecdot.rs:96-157) and allclose_all with TE = f64 (isclose.rs:92-106) for the
+    half and complex types: against complex128 / f64 sums, tolerance = rounding of the element type."""
+    rng = np.random.default_rng(seed_of(("extdot", _name(dt))))
+    a, b = _data(rng, 64 * 300, dt).reshape(64, 300), _data(rng, 64 * 300, dt).reshape(64, 300)
+    ta, tb = rt.asarray(a.reshape(-1), dev).reshape([64, 300]), rt.asarray(b.reshape(-1), dev).reshape([64, 300])
+    cplx = np.dtype(dt).kind == "c"
+    wide = np.complex128 if cplx else np.float64
+    tol = {"float16": 2e-3, "bfloat16": 2e-2, "complex64": 2e-5, "complex128": 1e-12}[_name(dt)]
+    for axis, npaxis in ((-1, 1), (0, 0)):
+        got = rt.vecdot(ta, tb, axis=axis)
+        assert got.dtype == np.dtype(dt)
+        want = np.sum(np.conj(a.astype(wide)) * b.astype(wide), axis=npaxis)
+        scale = np.sum(np.abs(a.astype(wide)) * np.abs(b.astype(wide)), axis=npaxis)
+        assert np.all(np.abs(got.to_numpy().astype(wide) - want) <= tol * scale), (dt, axis)
+    assert rt.allclose(ta, ta)
+    c = a.copy()
+    c[17, 123] = c[17, 123] * dt(1.5) + dt(1)
+    tc = rt.asarray(c.reshape(-1), dev).reshape([64, 300])
+    assert not rt.allclose(ta, tc)
+    assert rt.allclose(ta, tc, rtol=10.0, atol=10.0)
+    n = a.copy()
+    n[3, 4] = np.nan
+    tn = rt.asarray(n.reshape(-1), dev).reshape([64, 300])
+    assert not rt.allclose(tn, tn)
+    assert rt.allclose(tn, tn, equal_nan=True)
+
+
+def test_creation_of_half_and_complex(dev):
+    """linspace in the element type's own arithmetic (start + T::from(i) * step, cpu_rayon/creation.rs:108-131), the serial
+    arange recurrence of the 8- / 16-bit types (cpu_serial/creation.rs:7-19) and tril on 16-byte elements."""
+    # complex: (end - start) / Complex::from(n - 1) is the textbook quotient, i * step the textbook product
+    for dt, rdt in ((np.complex64, np.float32), (np.complex128, np.float64)):
+        s, e, n = dt(1.0 + 2.0j), dt(3.5 + 4.7j), 10          # the reference's own linspace_impl test values
+        got = dev.to_cpu_vec(dev.linspace_impl(s, e, n, True, dt))
+        step = _cdiv(np.array([e - s], dtype=dt), np.array([n - 1 + 0j], dtype=dt))
+        want = np.array([s + _cmul(np.array([i + 0j], dtype=dt), step)[0] for i in range(n)], dtype=dt)
+        assert _same_bits(got, want), dt
+        assert got[0] == s and abs(got[-1] - e) <= 4 * np.finfo(rdt).eps * abs(e)
+        got = dev.to_cpu_vec(dev.linspace_impl(s, e, 7, False, dt))
+        assert len(got) == 7 and abs(got[-1] - (s + (e - s) * 6 / 7)) <= 8 * np.finfo(rdt).eps * abs(e)
+    for hdt in HALF:
+        f = lambda x: np.float32(x)
+        s, e, n = hdt(-2.0), hdt(3.0), 33
+        got = dev.to_cpu_vec(dev.linspace_impl(s, e, n, True, hdt))
+        step = hdt(f(hdt(f(e) - f(s))) / f(hdt(f(n - 1))))
+        want = np.array([hdt(f(s) + f(hdt(f(hdt(f(i))) * f(step)))) for i in range(n)], dtype=hdt)
+        assert _same_bits(got, want), hdt
+        # arange: current = current + step rounded to the half type at every step
+        got = dev.to_cpu_vec(dev.arange_impl(hdt(0.0), hdt(2.0), hdt(0.1), hdt))
+        want, cur = [], hdt(0.0)
+        while f(cur) < f(hdt(2.0)):
+            want.append(cur)
+            cur = hdt(f(cur) + f(hdt(0.1)))
+        assert _same_bits(got, np.array(want, dtype=hdt)), hdt
+    for idt in (np.int8, np.uint8, np.int16, np.uint16):
+        got = dev.to_cpu_vec(dev.arange_impl(3, 100, 7, idt))
+        assert got.dtype == np.dtype(idt) and np.array_equal(got, np.arange(3, 100, 7, dtype=idt))
+    assert len(dev.to_cpu_vec(dev.arange_impl(5, 5, 1, np.int16))) == 0
+    z = _data(np.random.default_rng(5), 6 * 9, np.complex128).reshape(6, 9)
+    raw = upload(dev, z.reshape(-1).copy())
+    dev.tril_impl(raw, rt.Layout((6, 9), (9, 1)), 1)
+    assert _same_bits(dev.to_cpu_vec(raw).reshape(6, 9), np.tril(z, 1))
