@@ -78,7 +78,7 @@ typedef enum rc_dtype {
      * :368-545; a half type pairs with itself and bool only, as there); + - * / neg, comparisons (== != only for complex),
      * maximum / minimum and the float math functions for half; abs / real / imag (real output), conj, square, reciprocal and
      * every ComplexFloat function of the reference for complex (exp log log2 log10 sqrt sin cos tan asin acos atan sinh
-     * cosh tanh asinh acosh atanh; is_nan / is_infinite / is_finite); reductions sum / prod / mean / var / std / l2_norm
+     * cosh tanh asinh acosh atanh; sign = z / |z|; is_nan / is_infinite / is_finite); elementwise isclose; reductions sum / prod / mean / var / std / l2_norm
      * (all four; var / std / l2_norm of complex are real), max / min / argmin / argmax / count_nonzero (half); vecdot
      * (sum conj(a) b), allclose_all; linspace (all four, in the type's own arithmetic), arange (half: the reference's
      * serial recurrence), tril / triu.

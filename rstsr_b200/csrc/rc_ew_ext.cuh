@@ -53,6 +53,32 @@ RC_CPLX_MATH(FCAtanh, thrust::atanh(z))
 // num-complex: log2 / log10 = ln(z) scaled by 1 / ln(base) on both components (Complex::log(base) via to_polar)
 RC_CPLX_MATH(FCLog2, thrust::log(z) / thrust::complex<R>((R)0.693147180559945309417232121458176568))
 RC_CPLX_MATH(FCLog10, thrust::log(z) / thrust::complex<R>((R)2.302585092994045684017991454684364208))
+// ext_sign of a complex number: z / |z| (componentwise division by the real norm), zero for a zero magnitude
+// (rstsr-dtype-traits/src/ext_num.rs:268-280)
+template <class R> struct FCSign { using TA = cplx<R>; using TB = TA; using TO = TA; static constexpr int NIN = 1;
+    RC_FN TA apply(TA a) {
+        R n;
+        if constexpr (sizeof(R) == 4) n = hypotf(a.re, a.im); else n = hypot(a.re, a.im);
+        return n == (R)0 ? TA((R)0, (R)0) : TA(a.re / n, a.im / n); } };
+// elementwise isclose for half / complex (isclose.rs:92-106, TE = f64): |a - b| and |b| in the element type, then widened
+template <class T> struct FIsCloseX { using TA = T; using TB = T; using TO = uint8_t; static constexpr int NIN = 2;
+    using Params = IsCloseParams;
+    RC_FN uint8_t apply(T a, T b, const IsCloseParams &p) {
+        double diff, abs_b;
+        bool both_nan;
+        if constexpr (is_cplx_t<T>::value) {
+            using R = typename real_of<T>::type;
+            const T df = a - b;
+            if constexpr (sizeof(R) == 4) { diff = (double)hypotf(df.re, df.im); abs_b = (double)hypotf(b.re, b.im); }
+            else { diff = hypot(df.re, df.im); abs_b = hypot(b.re, b.im); }
+            both_nan = (a.re != a.re || a.im != a.im) && (b.re != b.re || b.im != b.im);
+        } else {
+            const float df = (a - b).f(), fb = b.f();
+            diff = (double)fabsf(df);
+            abs_b = (double)fabsf(fb);
+            both_nan = a.f() != a.f() && fb != fb;
+        }
+        return (diff <= p.atol + p.rtol * abs_b || (p.equal_nan && both_nan)) ? 1 : 0; } };
 // predicates (num-complex): is_nan = re or im NaN; is_infinite = not NaN and re or im infinite; is_finite = both finite
 template <class R> struct FCIsNan { using TA = cplx<R>; using TB = TA; using TO = uint8_t; static constexpr int NIN = 1;
     RC_FN uint8_t apply(TA a) { return (a.re != a.re) || (a.im != a.im); } };

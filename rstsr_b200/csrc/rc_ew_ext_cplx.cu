@@ -40,13 +40,23 @@ bool run_unary_cplx(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, co
             RC_CPLX_UN(RC_TANH, FCTanh) RC_CPLX_UN(RC_TAN, FCTan) RC_CPLX_UN(RC_ASIN, FCAsin) RC_CPLX_UN(RC_ACOS, FCAcos)
             RC_CPLX_UN(RC_ATAN, FCAtan) RC_CPLX_UN(RC_ASINH, FCAsinh) RC_CPLX_UN(RC_ACOSH, FCAcosh) RC_CPLX_UN(RC_ATANH, FCAtanh)
             RC_CPLX_UN(RC_LOG2, FCLog2) RC_CPLX_UN(RC_LOG10, FCLog10)
-            RC_CPLX_UN(RC_ISNAN, FCIsNan) RC_CPLX_UN(RC_ISINF, FCIsInf) RC_CPLX_UN(RC_ISFINITE, FCIsFinite)
+            RC_CPLX_UN(RC_SIGN, FCSign) RC_CPLX_UN(RC_ISNAN, FCIsNan) RC_CPLX_UN(RC_ISINF, FCIsInf) RC_CPLX_UN(RC_ISFINITE, FCIsFinite)
             default: break;
         }
     }
 #undef RC_CPLX_UN
 #undef RC_CPLX_UN_T
     return false;
+}
+
+bool run_isclose_ext(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args) {
+    switch (t) {
+        case RC_F16: ew_launch<FIsCloseX<h16>>(dev, c, args); return true;
+        case RC_BF16: ew_launch<FIsCloseX<b16>>(dev, c, args); return true;
+        case RC_C32: ew_launch<FIsCloseX<c32>>(dev, c, args); return true;
+        case RC_C64: ew_launch<FIsCloseX<c64>>(dev, c, args); return true;
+        default: return false;
+    }
 }
 
 }  // namespace rc

@@ -28,7 +28,10 @@ void run_binary_pow_mixed(rc_device *dev, rc_dtype t, const CanonEw &c, const Ew
 }
 
 // elementwise isclose, bool output; args.params -> IsCloseParams
+bool run_isclose_ext(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args);  // rc_ew_ext_cplx.cu
+
 void run_isclose(rc_device *dev, rc_dtype t, const CanonEw &c, const EwArgs &args) {
+    if (dtype_is_extended(t) && run_isclose_ext(dev, t, c, args)) return;
     switch (t) {
         RC_SWITCH_NUM(FIsClose)
         default: break;

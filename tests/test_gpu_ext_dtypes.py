@@ -423,3 +423,39 @@ def test_creation_of_half_and_complex(dev):
     raw = upload(dev, z.reshape(-1).copy())
     dev.tril_impl(raw, rt.Layout((6, 9), (9, 1)), 1)
     assert _same_bits(dev.to_cpu_vec(raw).reshape(6, 9), np.tril(z, 1))
+
+
+@pytest.mark.parametrize("dt", ALL, ids=_name)
+def test_elementwise_isclose_and_complex_sign(dev, dt):
+    """OpIsCloseAPI on half / complex operands (TE = f64; |a - b| and |b| formed in the element type) and ext_sign of
+    complex numbers: z / |z|, zero for zero (ext_num.rs:268-280)."""
+    rng = np.random.default_rng(seed_of(("extclose", _name(dt))))
+    a = _data(rng, 3000, dt)
+    b = a.copy()
+    b[::3] = (b[::3].astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64) * 1.01).astype(dt)
+    b[5] = np.nan
+    a[5] = np.nan
+    rtol, atol = 5e-3, 1e-3
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    if np.dtype(dt).kind == "c":
+        diff = np.abs((a - b)).astype(np.float64)
+    else:
+        diff = np.abs((a.astype(np.float32) - b.astype(np.float32)).astype(dt).astype(np.float64))
+    with np.errstate(invalid="ignore"):
+        want = diff <= atol + rtol * np.abs(b.astype(wide))
+    for equal_nan in (False, True):
+        w = want.copy()
+        w[5] = equal_nan
+        got = rt.isclose(rt.asarray(a, dev), rt.asarray(b, dev), rtol=rtol, atol=atol, equal_nan=equal_nan).to_numpy()
+        # entries within one rounding of the threshold may fall either way (hypot / the half rounding of a - b)
+        edge = np.abs(diff - (atol + rtol * np.abs(b.astype(wide)))) <= 1e-3 * (atol + rtol * np.abs(b.astype(wide)))
+        edge[5] = False
+        assert np.array_equal(got[~edge], w[~edge]), (dt, equal_nan)
+    if np.dtype(dt).kind == "c":
+        z = a.copy()
+        z[5] = 0
+        z[6] = complex(0.0, -2.0)
+        got = rt.asarray(z, dev).unary("sign").to_numpy()
+        n = np.abs(z)
+        want = np.where(n == 0, 0, z / np.where(n == 0, 1, n)).astype(dt)
+        assert got[5] == 0 and np.allclose(got, want, rtol=4 * np.finfo(z.real.dtype).eps, atol=0)
