@@ -20,6 +20,11 @@ bool run_binary_cplx(rc_device *dev, rc_binop op, rc_dtype t, const CanonEw &c, 
     return false;
 }
 
+// thrust-based functions live in two translation units of their own (rc_ew_ext_cplx_math{1,2}.cu: they dominate the
+// compile time) and skip the tile kernels: a transposed complex operand of a transcendental function takes the flat kernel
+bool run_unary_cplx_math1(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+bool run_unary_cplx_math2(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args);
+
 bool run_unary_cplx(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, const EwArgs &args) {
 #define RC_CPLX_UN(OPCODE, FF)                                                  \
     case OPCODE:                                                                \
@@ -35,14 +40,11 @@ bool run_unary_cplx(rc_device *dev, rc_unop op, rc_dtype t, const CanonEw &c, co
         switch (op) {
             RC_CPLX_UN_T(RC_NEG, FNeg) RC_CPLX_UN_T(RC_SQUARE, FSquare)
             RC_CPLX_UN(RC_ABS, FCAbs) RC_CPLX_UN(RC_REAL, FCReal) RC_CPLX_UN(RC_IMAG, FCImag) RC_CPLX_UN(RC_CONJ, FCConj)
-            RC_CPLX_UN(RC_RECIPROCAL, FCRecip) RC_CPLX_UN(RC_EXP, FCExp) RC_CPLX_UN(RC_LOG, FCLog) RC_CPLX_UN(RC_SQRT, FCSqrt)
-            RC_CPLX_UN(RC_SIN, FCSin) RC_CPLX_UN(RC_COS, FCCos) RC_CPLX_UN(RC_SINH, FCSinh) RC_CPLX_UN(RC_COSH, FCCosh)
-            RC_CPLX_UN(RC_TANH, FCTanh) RC_CPLX_UN(RC_TAN, FCTan) RC_CPLX_UN(RC_ASIN, FCAsin) RC_CPLX_UN(RC_ACOS, FCAcos)
-            RC_CPLX_UN(RC_ATAN, FCAtan) RC_CPLX_UN(RC_ASINH, FCAsinh) RC_CPLX_UN(RC_ACOSH, FCAcosh) RC_CPLX_UN(RC_ATANH, FCAtanh)
-            RC_CPLX_UN(RC_LOG2, FCLog2) RC_CPLX_UN(RC_LOG10, FCLog10)
-            RC_CPLX_UN(RC_SIGN, FCSign) RC_CPLX_UN(RC_ISNAN, FCIsNan) RC_CPLX_UN(RC_ISINF, FCIsInf) RC_CPLX_UN(RC_ISFINITE, FCIsFinite)
+            RC_CPLX_UN(RC_RECIPROCAL, FCRecip) RC_CPLX_UN(RC_SIGN, FCSign)
+            RC_CPLX_UN(RC_ISNAN, FCIsNan) RC_CPLX_UN(RC_ISINF, FCIsInf) RC_CPLX_UN(RC_ISFINITE, FCIsFinite)
             default: break;
         }
+        return run_unary_cplx_math1(dev, op, t, c, args) || run_unary_cplx_math2(dev, op, t, c, args);
     }
 #undef RC_CPLX_UN
 #undef RC_CPLX_UN_T
