@@ -347,6 +347,93 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_rows_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// column reduction over a FEW rows (n_red <= RED_SMALL_ROWS: sums over xyz components, small batch axes).  The general
+// column kernel gives such a launch 256 columns x n_red rows per CTA -- a few KB -- and pays a shared-memory fold and a
+// barrier for row-lanes that have nothing to do: (3, n) f64 sum axis 0 ran at 1.9 TB/s.  Here a thread owns CPT column
+// packs, walks all rows itself (CPT loads in flight per row step, 4 row steps unrolled for narrow loads) and writes the
+// results: no shared memory, no barrier, 4 x the bytes per CTA.
+constexpr int RED_SMALL_ROWS = 16;
+template <class TI, int VEC> __host__ __device__ constexpr int red_small_cpt() { return 4; }  // 8 for narrow loads: (3, n) f64 5.4 -> 2.3 TB/s
+template <class P, int VEC, bool MULTI>
+__global__ void __launch_bounds__(RED_BLOCK) reduce_cols_small_kernel(const __grid_constant__ RedDesc d,
+                                                                      const typename P::TI *__restrict__ in,
+                                                                      const typename P::TI *__restrict__ in2,
+                                                                      typename P::TO *__restrict__ out) {
+    using TI = typename P::TI;
+    using S = typename P::S;
+    using TO = typename P::TO;
+    constexpr bool BIN = is_binary<P>::value;
+    constexpr int CPT = red_small_cpt<TI, VEC>();
+    const int64_t total = d.packs0 * d.n_out;  // column packs over all kept dims
+    const int64_t base = (int64_t)blockIdx.x * (RED_BLOCK * CPT) + threadIdx.x;
+    const TI *src[CPT];
+    const TI *src2[CPT];
+    int64_t off_out[CPT];
+    bool valid[CPT];
+    S acc[CPT][VEC];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int64_t g = base + (int64_t)c * RED_BLOCK;
+        valid[c] = g < total;
+        src[c] = in; src2[c] = in2; off_out[c] = 0;
+        if (valid[c]) {
+            const int64_t kb = g / d.packs0, col = g - kb * d.packs0;
+            src[c] = in + col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in, d.big);
+            if constexpr (BIN) src2[c] = in2 + col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_in2, d.big);
+            off_out[c] = col * VEC + decompose(kb, 1, d.nk, d.kshape, d.kdiv, d.ks_out, d.big);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[c][j] = P::init();
+    }
+    const int64_t rs0 = d.rs[0], rs20 = BIN ? d.rs2[0] : 0;
+    const int n = (int)d.n_items;
+    constexpr int RU = VEC * sizeof(TI) >= 16 ? 1 : 4;
+#pragma unroll(RU)
+    for (int r = 0; r < n; ++r) {
+        int64_t off, off2 = 0;
+        if constexpr (MULTI) {
+            off = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs, d.big);
+            if constexpr (BIN) off2 = decompose(r, 0, d.nr, d.rshape, d.rdiv, d.rs2, d.big);
+        } else {
+            off = r * rs0;
+            off2 = r * rs20;
+        }
+        Pack<TI, VEC> p[CPT];
+        Pack<TI, VEC> q[BIN ? CPT : 1];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            if (valid[c]) {
+                p[c] = ld_stream<TI, VEC>(src[c] + off);
+                if constexpr (BIN) q[c] = ld_stream<TI, VEC>(src2[c] + off2);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            if (valid[c]) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if constexpr (BIN) acc[c][j] = P::comb(acc[c][j], P::pre2(p[c].v[j], q[c].v[j], d));
+                    else fold<P>(acc[c][j], p[c].v[j], (int64_t)r);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        if (!valid[c]) continue;
+        Pack<TO, VEC> o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o.v[j] = P::fin(acc[c][j], d.n_red);
+        if constexpr (VEC > 1 && (VEC * sizeof(TO) == 16 || VEC * sizeof(TO) == 32)) {
+            st_stream<TO, VEC>(out + off_out[c], o);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) out[off_out[c] + j] = o.v[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <class P, int VEC, bool MULTI>
 __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_constant__ RedDesc d,
                                                                 const typename P::TI *__restrict__ in,
@@ -357,7 +444,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_cols_kernel(const __grid_con
     using S = typename P::S;
     using TO = typename P::TO;
     constexpr bool BIN = is_binary<P>::value;
-    constexpr int U = BIN ? RED_UNROLL / 2 : RED_UNROLL;
+    constexpr int U = BIN ? RED_UNROLL / 2 : RED_UNROLL;  // (16 for scalar loads was tried: the longer tail loses 35 %)
     extern __shared__ __align__(32) unsigned char red_smem[];
     S *sm = reinterpret_cast<S *>(red_smem);  // [RW][TC][VEC]
     const int TC = d.tcol, RW = RED_BLOCK / TC;
@@ -675,6 +762,30 @@ void launch_cols(rc_device *dev, const RedDesc &d, int vec, int64_t sy, const ty
     after_launch(dev, "reduce_cols_kernel");
 }
 
+template <class P, int V>
+bool launch_cols_small(rc_device *dev, const RedDesc &d, int vec, const typename P::TI *in, const typename P::TI *in2,
+                       typename P::TO *out) {
+    static const bool off = [] { const char *e = getenv("RC_COLS_SMALL"); return e && e[0] == '0'; }();
+    using TI = typename P::TI;
+    const int64_t total = d.packs0 * d.n_out;
+    const int64_t per_cta = (int64_t)RED_BLOCK * (vec > 1 ? red_small_cpt<TI, V>() : red_small_cpt<TI, 1>());
+    const int64_t gx = (total + per_cta - 1) / per_cta;
+    if (off || gx >= (1ll << 31)) return false;
+    const bool multi = d.nr > 1;
+    if constexpr (V > 1) {
+        if (vec > 1) {
+            if (multi) reduce_cols_small_kernel<P, V, true><<<(unsigned)gx, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out);
+            else reduce_cols_small_kernel<P, V, false><<<(unsigned)gx, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out);
+            after_launch(dev, "reduce_cols_small_kernel");
+            return true;
+        }
+    }
+    if (multi) reduce_cols_small_kernel<P, 1, true><<<(unsigned)gx, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out);
+    else reduce_cols_small_kernel<P, 1, false><<<(unsigned)gx, RED_BLOCK, 0, dev->stream>>>(d, in, in2, out);
+    after_launch(dev, "reduce_cols_small_kernel");
+    return true;
+}
+
 // threads along the kept (contiguous) axis of the column kernel; RC_TCOL_MAX is a tuning knob for experiments
 inline int tcol_max() {
     static int v = [] { const char *e = getenv("RC_TCOL_MAX"); int x = e ? atoi(e) : 64; return (x >= 1 && x <= RED_BLOCK) ? x : 64; }();
@@ -763,7 +874,18 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         // threads along the kept axis: 64 (4 warp-rows walk the reduced rows) unless the reduced extent is too short to
         // keep RED_UNROLL loads per thread in flight -- then fewer row-lanes, down to one thread per column pack
         // ((4, 2^24) sum axis 0: 2.3 -> TB/s measured with the fixed 64)
-        const int64_t rw_want = std::max<int64_t>(1, std::min<int64_t>(RED_BLOCK / tcol_max(), pow2_floor(std::max<int64_t>(1, n_red / RED_UNROLL))));
+        d.n_out = n_out / d.kshape[0];
+        d.n_items = n_red;
+        if (n_red >= (1ll << 31) || d.n_out >= (1ll << 31)) d.big = 1;
+        // a few rows: one thread per column pack, no row-lanes (reduce_cols_small_kernel).  Up to 4 rows always (2 rows
+        // +29 %, 3 rows 2.8x); 5..16 rows only when the kept rows are short, where the general kernel's 64-column tiles
+        // do not fill ((32768,16,256) f32 +62 %; (8, 2^24) and (256,16,32768) are 4 % better on the general kernel)
+        if (n_red <= 4 || (n_red <= RED_SMALL_ROWS && d.packs0 <= 128)) {
+            d.to_partial = 0;
+            if (launch_cols_small<P, V>(dev, d, vec, in, in2, out)) return;
+        }
+        const int64_t unroll = RED_UNROLL;
+        const int64_t rw_want = std::max<int64_t>(1, std::min<int64_t>(RED_BLOCK / tcol_max(), pow2_floor(std::max<int64_t>(1, n_red / unroll))));
         d.tcol = (int)std::min<int64_t>(RED_BLOCK / rw_want, pow2_ceil(d.packs0));
         d.n_out = n_out / d.kshape[0];
         d.n_items = n_red;
@@ -771,7 +893,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         const int rw = RED_BLOCK / d.tcol;
         int64_t base_ctas = ((d.packs0 + d.tcol - 1) / d.tcol) * d.n_out;
         int64_t Sx = std::min<int64_t>(std::max<int64_t>(1, target_ctas / base_ctas),
-                                       std::max<int64_t>(1, n_red / ((int64_t)rw * RED_UNROLL * 2)));
+                                       std::max<int64_t>(1, n_red / ((int64_t)rw * unroll * 2)));
         Sx = std::max<int64_t>(1, std::min<int64_t>(Sx, 1024));
         d.chunk = (n_red + Sx - 1) / Sx;
         Sx = (n_red + d.chunk - 1) / d.chunk;

@@ -162,13 +162,24 @@ RED_SHAPES = [
     ("generic (no unit stride)", (30, 40, 10), "stepped"),
     ("reduce everything via axes", (64, 64, 16), [0, 1, 2]),
     ("tiny", (3, 2), [0]),
+    # few reduced rows over a contiguous kept axis: reduce_cols_small_kernel (one thread per column pack, no row-lanes)
+    ("small rows 3 x packs", (3, 4096), [0]),
+    ("small rows 3 x odd columns (scalar)", (3, 4099), [0]),
+    ("small rows 2, kept outer", (50, 2, 1028), [1]),
+    ("small rows 4, kept outer, odd columns", (9, 4, 333), [1]),
+    ("small rows multi-dim reduced (2 x 3)", (2, 7, 3, 260), [0, 2]),
+    ("small rows 16 x short kept rows", (300, 16, 64), [1]),
+    ("small rows 1", (1, 5000), [0]),
+    ("17 rows: general column kernel", (17, 5000), [0]),
 ]
 
 
 @pytest.mark.parametrize("name,shape,axes", RED_SHAPES, ids=[r[0] for r in RED_SHAPES])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
-@pytest.mark.parametrize("op", ["sum", "max"])
+@pytest.mark.parametrize("op", ["sum", "max", "mean"])
 def test_reduce_kernel_variants(dev, name, shape, axes, dtype, op):
+    if op == "mean" and np.dtype(dtype).kind != "f":
+        pytest.skip("mean of integers is not supported by the reference (numpy_differences.md:234-244)")
     rng = np.random.default_rng(seed_of(name, op))
     n = int(np.prod(shape))
     a = rand_data(rng, n, dtype)
