@@ -161,29 +161,36 @@ template <bool ALL> struct PLogic {  // all / any over bool (auto_impl/reduction
 template <class T> struct alignas(16) ArgState { T v; int64_t i; };  // i < 0: empty ("None")
 // argmin / argmax: first occurrence in row-major order wins; NaN is never accepted unless it is element 0
 // (f_comp(None, y) = true, y < NaN = false: cpu_serial/reduction.rs:436-470) -- reproduced order-independently.
+// The reference takes element 0 unconditionally and then only strictly better values.  Here an EMPTY state carries the
+// worst value of the type (lowest for max, largest for min), so "strictly better than the accumulator" is the whole test
+// in the inner loop (the first version tested emptiness, NaN and the index per element: 30 instructions per element,
+// 109 registers, 2 CTAs per SM, 3.9 TB/s on an (8192, 8192) f64 argmax over rows -- ncu).  Elements equal to the worst
+// value are therefore never taken; if nothing is, the result is still empty and the answer is index 0 -- exactly what the
+// reference returns when no element is strictly better than element 0.  A NaN in element 0 is taken (and sticks).
 template <class T, bool MAX> struct PArg {
     using TI = T; using S = ArgState<T>; using TO = uint64_t; using Second = PState<PArg<T, MAX>>;
     static __device__ __forceinline__ bool isnan_(T x) { return x != x; }
-    static __device__ __forceinline__ S init() { return S{(T)0, -1}; }
-    static __device__ __forceinline__ S pre(T x, int64_t idx) { return (isnan_(x) && idx != 0) ? S{(T)0, -1} : S{x, idx}; }
+    static __device__ __forceinline__ T worst() {
+        if constexpr (std::is_floating_point<T>::value) return MAX ? -INFINITY : INFINITY;
+        else return MAX ? std::numeric_limits<T>::lowest() : std::numeric_limits<T>::max();
+    }
+    static __device__ __forceinline__ S init() { return S{worst(), -1}; }
+    static __device__ __forceinline__ S pre(T x, int64_t idx) { return (isnan_(x) && idx != 0) ? init() : S{x, idx}; }
     static __device__ __forceinline__ S comb(S a, S b) {
-        if (a.i < 0) return b;
-        if (b.i < 0) return a;
         if (isnan_(a.v)) return a;  // only global element 0 can carry NaN: it sticks
         if (isnan_(b.v)) return b;
         const bool b_better = MAX ? (b.v > a.v) : (b.v < a.v);
         const bool a_better = MAX ? (a.v > b.v) : (a.v < b.v);
         if (b_better) return b;
         if (a_better) return a;
-        return (b.i < a.i) ? b : a;
+        return ((uint64_t)b.i < (uint64_t)a.i) ? b : a;  // tie: first occurrence; an empty state (i = -1) loses
     }
-    static __device__ __forceinline__ TO fin(S s, int64_t) { return (uint64_t)s.i; }
-    // In-thread accumulation: every accumulator sees strictly increasing indices, so a strict comparison keeps the
-    // first occurrence and `comb`'s tie / NaN cases reduce to "an empty slot takes anything but a late NaN".
+    static __device__ __forceinline__ TO fin(S s, int64_t) { return s.i < 0 ? (uint64_t)0 : (uint64_t)s.i; }
+    // In-thread accumulation: every accumulator sees strictly increasing indices, so the strict comparison keeps the
+    // first occurrence; it is false for a NaN element and once the accumulator holds the NaN of element 0.
     static __device__ __forceinline__ void update(S &a, T x, int64_t idx) {
         const bool better = MAX ? (x > a.v) : (x < a.v);
-        const bool take = (a.i < 0) ? !(isnan_(x) && idx != 0) : better;
-        if (take) { a.v = x; a.i = idx; }
+        if (better || (isnan_(x) && idx == 0)) { a.v = x; a.i = idx; }
     }
 };
 

@@ -53,6 +53,42 @@ def test_arg_nan_rule(dev):
     assert e.value.kind == "InvalidLayout"
 
 
+def test_arg_worst_value_rows(dev):
+    """Rows whose extreme IS the type's worst value (the empty accumulator of the kernels carries it): all -inf / +inf,
+    all INT_MIN / INT_MAX, NaN in front of them, long rows split over many threads and both kernel families (rows, columns)
+    -- the answer is the reference's fold (element 0 unconditionally, then strictly better values only)."""
+    import oracle
+    cases = []
+    for n in (5, 300, 5000):
+        cases += [np.full(n, -np.inf), np.full(n, np.inf), np.r_[np.nan, np.full(n - 1, -np.inf)],
+                  np.r_[-np.inf, np.nan, np.full(n - 2, -np.inf)], np.r_[np.full(n - 1, -np.inf), 1.0],
+                  np.r_[np.nan, np.arange(n - 1.0)], np.r_[np.full(n // 2, np.inf), -np.inf, np.full(n - n // 2 - 1, np.inf)]]
+    for row in cases:
+        for dt in (np.float64, np.float32):
+            v = row.astype(dt)
+            t = rt.asarray(v, dev)
+            for op, is_max in (("argmax", True), ("argmin", False)):
+                want = oracle._arg_fold(list(v), is_max)
+                assert getattr(t, op + "_all")() == want, (op, dt, len(v), v[:3])
+                # the same row as one of many rows (rows kernel) and as one of many columns (column kernels)
+                m = np.tile(v, (7, 1))
+                tm = rt.asarray(m.reshape(-1), dev).reshape([7, len(v)])
+                assert getattr(tm, op + "_axes")(1).to_numpy().tolist() == [want] * 7
+                tc = rt.asarray(np.ascontiguousarray(m.T).reshape(-1), dev).reshape([len(v), 7])
+                assert getattr(tc, op + "_axes")(0).to_numpy().tolist() == [want] * 7
+    for dt in (np.int32, np.int64, np.uint32):
+        info = np.iinfo(dt)
+        for n in (4, 3000):
+            for fillv in (info.min, info.max):
+                v = np.full(n, fillv, dtype=dt)
+                t = rt.asarray(v, dev)
+                assert t.argmax_all() == 0 and t.argmin_all() == 0
+                v[n // 2] = 7 if fillv == info.min else 3
+                t = rt.asarray(v, dev)
+                assert t.argmax_all() == (n // 2 if fillv == info.min else 0)
+                assert t.argmin_all() == (n // 2 if fillv == info.max else 0)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("op", ["var", "std", "l2_norm"])
 def test_float_moments_random_views(dev, op, dtype):
