@@ -809,9 +809,11 @@ int pow2_floor(int64_t x) { int p = 1; while ((int64_t)p * 2 <= x) p *= 2; retur
 int pow2_ceil(int64_t x) { int p = 1; while (p < x) p *= 2; return p; }
 
 // P: first-pass policy.  The second pass (over partial states) uses P::Second (P itself when pre is the identity).
-template <class P>
-void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, int64_t n_red_logical,
-                  const void *b_v = nullptr, double fp0 = 0.0, double fp1 = 0.0, int ip0 = 0) {
+// V = elements per pack of the vector variants this instantiation may launch (it falls back to one element per load
+// when extents / strides / pointers rule the packs out); see reduce_typed below for how V is chosen
+template <class P, int V>
+void reduce_typed_w(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, int64_t n_red_logical,
+                    const void *b_v = nullptr, double fp0 = 0.0, double fp1 = 0.0, int ip0 = 0) {
     using TI = typename P::TI;
     using S = typename P::S;
     using TO = typename P::TO;
@@ -822,7 +824,6 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     const TI *in = static_cast<const TI *>(a_v) + c.base_in;
     const TI *in2 = BIN ? static_cast<const TI *>(b_v) + c.base_in2 : nullptr;
     TO *out = static_cast<TO *>(out_v) + c.base_out;
-    constexpr int V = 32 / sizeof(TI);        // 256-bit packs of the element type
     constexpr bool SIMPLE = std::is_same<P2, P>::value;  // state == element, pre == identity
     const int64_t n_out = c.n_out(), n_red = c.n_red();
     // two FULL waves at the kernels' occupancy (4 CTAs of 256 threads per SM at <= 64 registers): a split that
@@ -868,11 +869,11 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
 
     if (!red_contig && kept_contig && n_red > 0) {
         // ---------------- column kernel ----------------
-        bool vec_ok = V > 1 && d.kshape[0] % V == 0 && aligned_bytes(in, 32) && aligned_bytes(out, V * sizeof(TO));
+        bool vec_ok = V > 1 && d.kshape[0] % V == 0 && aligned_bytes(in, V * sizeof(TI)) && aligned_bytes(out, V * sizeof(TO));
         for (int i = 1; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0 && d.ks_out[i] % V == 0;
         for (int i = 0; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
         if constexpr (BIN) {
-            vec_ok = vec_ok && aligned_bytes(in2, 32);
+            vec_ok = vec_ok && aligned_bytes(in2, V * sizeof(TI));
             for (int i = 1; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in2[i] % V == 0;
             for (int i = 0; i < d.nr && vec_ok; ++i) vec_ok = d.rs2[i] % V == 0;
         }
@@ -916,7 +917,7 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
         // second pass: fold partial[S][n_out] over S, same kept dims with contiguous input strides
         RedDesc e = second_pass_desc(d, Sx);
         constexpr int V2 = SIMPLE ? V : 1;
-        const bool vec2 = V2 > 1 && vec_ok && (n_out % V2 == 0) && aligned_bytes(partial, 32);
+        const bool vec2 = V2 > 1 && vec_ok && (n_out % V2 == 0) && aligned_bytes(partial, V2 * sizeof(S));
         const int v2 = vec2 ? V2 : 1;
         e.packs0 = e.kshape[0] / v2;
         e.tcol = (int)std::min<int64_t>(tcol_max(), pow2_ceil(e.packs0));
@@ -925,11 +926,11 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
     }
 
     // ---------------- row kernel (contiguous or generic reduced space) ----------------
-    bool vec_ok = V > 1 && d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_bytes(in, 32);
+    bool vec_ok = V > 1 && d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % V == 0 && aligned_bytes(in, V * sizeof(TI));
     for (int i = 0; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in[i] % V == 0;
     for (int i = 1; i < d.nr && vec_ok; ++i) vec_ok = d.rs[i] % V == 0;
     if constexpr (BIN) {
-        vec_ok = vec_ok && d.rs2[0] == 1 && aligned_bytes(in2, 32);
+        vec_ok = vec_ok && d.rs2[0] == 1 && aligned_bytes(in2, V * sizeof(TI));
         for (int i = 0; i < d.nk && vec_ok; ++i) vec_ok = d.ks_in2[i] % V == 0;
         for (int i = 1; i < d.nr && vec_ok; ++i) vec_ok = d.rs2[i] % V == 0;
     }
@@ -1001,6 +1002,62 @@ void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_
 }
 
 // the five monoids of the hot path
+// Policies that also get HALF-width packs (16 bytes): sums / extrema / means of f32 and f64, where extents that are a
+// multiple of 4 but not of 8 elements (f32: 12, 20, 100 ...) or of 2 but not of 4 (f64) are common and the one-element path
+// costs a factor of 2-3 ((20971, 64, 100) f32 sum over axes (0, 2): 1.7 TB/s on the scalar path, 5.7 for f64 whose packs
+// fit).  Kept to these policies: every extra width is a full set of kernels per policy at build time.
+template <class P> struct half_packs : std::false_type {};
+template <> struct half_packs<PSum<float>> : std::true_type {};
+template <> struct half_packs<PSum<double>> : std::true_type {};
+template <> struct half_packs<PMax<float>> : std::true_type {};
+template <> struct half_packs<PMax<double>> : std::true_type {};
+template <> struct half_packs<PMin<float>> : std::true_type {};
+template <> struct half_packs<PMin<double>> : std::true_type {};
+template <> struct half_packs<PMean<float>> : std::true_type {};
+template <> struct half_packs<PMean<double>> : std::true_type {};
+
+// would packs of w elements pass the checks of reduce_typed_w?  (A wrong "yes" only costs the scalar fallback there.)
+template <class P>
+bool packs_fit(const CanonRed &c, const void *a_v, const void *b_v, const void *out_v, int w) {
+    using TI = typename P::TI;
+    using TO = typename P::TO;
+    constexpr bool BIN = is_binary<P>::value;
+    RedDesc d;
+    std::memset(&d, 0, sizeof(d));
+    fill_desc_dims(d, c);
+    const TI *in = static_cast<const TI *>(a_v) + c.base_in;
+    const TI *in2 = BIN ? static_cast<const TI *>(b_v) + c.base_in2 : nullptr;
+    const TO *out = static_cast<const TO *>(out_v) + c.base_out;
+    const bool red_contig = d.nr >= 1 && d.rs[0] == 1 && (!BIN || d.rs2[0] == 1) && d.rshape[0] >= 8;
+    const bool kept_contig = d.nk >= 1 && d.ks_in[0] == 1 && (!BIN || d.ks_in2[0] == 1) && d.ks_out[0] == 1 &&
+                             d.kshape[0] >= cols_min_extent();
+    bool ok = aligned_bytes(in, w * sizeof(TI)) && (!BIN || aligned_bytes(in2, w * sizeof(TI)));
+    if (!red_contig && kept_contig) {
+        ok = ok && d.kshape[0] % w == 0 && aligned_bytes(out, w * sizeof(TO));
+        for (int i = 1; i < d.nk && ok; ++i) ok = d.ks_in[i] % w == 0 && d.ks_out[i] % w == 0 && (!BIN || d.ks_in2[i] % w == 0);
+        for (int i = 0; i < d.nr && ok; ++i) ok = d.rs[i] % w == 0 && (!BIN || d.rs2[i] % w == 0);
+    } else {
+        ok = ok && d.nr >= 1 && d.rs[0] == 1 && d.rshape[0] % w == 0 && (!BIN || d.rs2[0] == 1);
+        for (int i = 0; i < d.nk && ok; ++i) ok = d.ks_in[i] % w == 0 && (!BIN || d.ks_in2[i] % w == 0);
+        for (int i = 1; i < d.nr && ok; ++i) ok = d.rs[i] % w == 0 && (!BIN || d.rs2[i] % w == 0);
+    }
+    return ok;
+}
+
+template <class P>
+void reduce_typed(rc_device *dev, const CanonRed &c, const void *a_v, void *out_v, int64_t n_red_logical,
+                  const void *b_v = nullptr, double fp0 = 0.0, double fp1 = 0.0, int ip0 = 0) {
+    constexpr int V = 32 / sizeof(typename P::TI);  // 256-bit packs of the element type
+    if constexpr (half_packs<P>::value && V >= 4) {
+        static const bool off = [] { const char *e = getenv("RC_RED_HALF_PACKS"); return e && e[0] == '0'; }();
+        if (!off && !c.empty_out && !packs_fit<P>(c, a_v, b_v, out_v, V) && packs_fit<P>(c, a_v, b_v, out_v, V / 2)) {
+            reduce_typed_w<P, V / 2>(dev, c, a_v, out_v, n_red_logical, b_v, fp0, fp1, ip0);
+            return;
+        }
+    }
+    reduce_typed_w<P, V>(dev, c, a_v, out_v, n_red_logical, b_v, fp0, fp1, ip0);
+}
+
 template <class T>
 void reduce_op(rc_device *dev, rc_redop op, const CanonRed &c, const void *a, void *out, int64_t n_red) {
     switch (op) {
