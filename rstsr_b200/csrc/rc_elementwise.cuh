@@ -76,7 +76,7 @@ __device__ __forceinline__ void ew_item_offsets(const EwDesc<3> &d, uint32_t idx
 // flat kernel.  F::NIN in {0 (fill), 1, 2}; F::apply(a[, b]) -> F::TO.  One-shot grid (measured on B200:
 // one-shot grids reach 6.8-7.0 TB/s on copy/add, persistent grid-stride loops 5.8-6.5 TB/s).
 // ---------------------------------------------------------------------------------------------
-template <class F, int VEC, int ND>
+template <class F, int VEC, int ND, int UN = EW_UNROLL>
 __global__ void __launch_bounds__(EW_BLOCK) ew_kernel(const __grid_constant__ EwDesc<3> d, typename F::TO *c, const typename F::TA *a,
                                                       const typename F::TB *b, int mode_a, int mode_b,
                                                       EwConst<typename F::TA> ka, EwConst<typename F::TB> kb,
@@ -84,21 +84,21 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_kernel(const __grid_constant__ Ew
     using TA = typename F::TA;
     using TB = typename F::TB;
     using TO = typename F::TO;
-    const uint32_t first = blockIdx.x * (EW_BLOCK * EW_UNROLL) + threadIdx.x;
+    const uint32_t first = blockIdx.x * (EW_BLOCK * UN) + threadIdx.x;
 
     // Straight-line code for every operand mode: packs start out as the constant, a predicated in-place
     // LDG overwrites them for memory operands, splat operands get a predicated scalar LDG and are selected
     // at the point of use.  All loads of the thread are issued before the first use.
-    Pack<TA, VEC> va[EW_UNROLL];
-    Pack<TB, VEC> vb[EW_UNROLL];
-    Pack<TA, 1> sa[EW_UNROLL];
-    Pack<TB, 1> sb[EW_UNROLL];
-    int64_t oc[EW_UNROLL];
-    bool ok[EW_UNROLL];
+    Pack<TA, VEC> va[UN];
+    Pack<TB, VEC> vb[UN];
+    Pack<TA, 1> sa[UN];
+    Pack<TB, 1> sb[UN];
+    int64_t oc[UN];
+    bool ok[UN];
     const bool mem_a = (F::NIN >= 1) && mode_a == MODE_MEM, spl_a = (F::NIN >= 1) && mode_a == MODE_SPLAT;
     const bool mem_b = (F::NIN >= 2) && mode_b == MODE_MEM, spl_b = (F::NIN >= 2) && mode_b == MODE_SPLAT;
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
+    for (int u = 0; u < UN; ++u) {
         const uint32_t idx = first + u * EW_BLOCK;
         ok[u] = idx < d.total;
         int64_t oa, ob;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(EW_BLOCK) ew_kernel(const __grid_constant__ Ew
         }
     }
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
+    for (int u = 0; u < UN; ++u) {
         if (ok[u]) {
             Pack<TO, VEC> r;
 #pragma unroll
@@ -882,6 +882,24 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
 
     auto stride_of = [&](int s, int i) -> int64_t { return s < 0 ? 0 : c.stride[s][i]; };
 
+    // ---- a long 1-D run whose length is not a multiple of the pack: packs for the body, elements for the tail (a flat f32
+    // add of 2^26 - 3 elements ran wholly on the one-element path: 5.9 TB/s against 6.7 with packs) ----
+    if constexpr (V > 1) {
+        if (c.ndim == 1 && c.shape[0] % V != 0 && c.shape[0] >= 64 * 1024 && c.stride[0][0] == 1) {
+            bool unit = true;
+            for (int s = 1; s < c.nops; ++s) unit = unit && (c.stride[s][0] == 1 || c.stride[s][0] == 0);
+            if (unit) {
+                CanonEw head = c, tail = c;
+                head.shape[0] = c.shape[0] - c.shape[0] % V;
+                tail.shape[0] = c.shape[0] % V;
+                for (int s = 0; s < c.nops; ++s) tail.base[s] = c.base[s] + head.shape[0] * c.stride[s][0];
+                ew_launch_part<F, ALLOW_TILE, ALLOW_VEC>(dev, head, args);
+                ew_launch_part<F, ALLOW_TILE, ALLOW_VEC>(dev, tail, args);
+                return;
+            }
+        }
+    }
+
     // ---- can dim 0 move as 16-byte packs? ----
     bool vec_ok = V > 1 && c.stride[0][0] == 1 && (c.shape[0] % V == 0) &&
                   (reinterpret_cast<uintptr_t>(pc) % (V * sizeof(TO)) == 0);
@@ -1196,9 +1214,14 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
             return;
         }
     }
-    // scalar path: element-rate bound, so 2-D problems take the compile-time rank (f32 a[:, 1:-1] copy 3.8 -> 5.45 TB/s)
-    if (c.ndim == 2) ew_kernel<F, 1, 2><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
-    else ew_kernel<F, 1, 0><<<grid, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
+    // scalar path: element-rate bound, so 2-D problems take the compile-time rank (f32 a[:, 1:-1] copy 3.8 -> 5.45 TB/s).
+    // Elements of <= 4 bytes: 8 instead of 4 items per thread -- 4 loads of 4 bytes per operand do not cover the memory
+    // latency (f32 add of operands one element off the pack alignment: 5.8 TB/s against 6.9 for f64)
+    constexpr bool NARROW = sizeof(TO) <= 4 && sizeof(TA) <= 4 && sizeof(TB) <= 4;
+    constexpr int UN = NARROW ? 2 * EW_UNROLL : EW_UNROLL;
+    const uint32_t grid1 = (uint32_t)((items + EW_BLOCK * UN - 1) / (EW_BLOCK * UN));
+    if (c.ndim == 2) ew_kernel<F, 1, 2, UN><<<grid1, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
+    else ew_kernel<F, 1, 0, UN><<<grid1, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
     after_launch(dev, "ew_kernel");
 }
 
