@@ -1221,6 +1221,7 @@ void ew_launch_part(rc_device *dev, const CanonEw &c, const EwArgs &args) {
     constexpr int UN = NARROW ? 2 * EW_UNROLL : EW_UNROLL;
     const uint32_t grid1 = (uint32_t)((items + EW_BLOCK * UN - 1) / (EW_BLOCK * UN));
     if (c.ndim == 2) ew_kernel<F, 1, 2, UN><<<grid1, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
+    else if (c.ndim == 1) ew_kernel<F, 1, 1, UN><<<grid1, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
     else ew_kernel<F, 1, 0, UN><<<grid1, EW_BLOCK, 0, dev->stream>>>(d, pc, pa, pb, mode_a, mode_b, ka, kb, prm);
     after_launch(dev, "ew_kernel");
 }
