@@ -893,7 +893,11 @@ void reduce_typed_w(rc_device *dev, const CanonRed &c, const void *a_v, void *ou
             if (launch_cols_small<P, V>(dev, d, vec, in, in2, out)) return;
         }
         const int64_t unroll = RED_UNROLL;
-        const int64_t rw_want = std::max<int64_t>(1, std::min<int64_t>(RED_BLOCK / tcol_max(), pow2_floor(std::max<int64_t>(1, n_red / unroll))));
+        // one element per load (extents / pointers rule the packs out): wider column tiles, so that a CTA still reads
+        // 512 B - 1 KB of every row it visits (sweep, scripts/probe_reduce_sweep.py with RC_TCOL_MAX: f32 (100, 1342177)
+        // axis 0 3.57 / 4.07 / 4.40 TB/s at 64 / 128 / 256 columns, f64 5.79 / 6.14 / 6.26; long reduced extents prefer 128)
+        const int tcol_limit = vec > 1 ? tcol_max() : std::max(tcol_max(), (sizeof(TI) <= 4 && n_red <= 512) ? 256 : 128);
+        const int64_t rw_want = std::max<int64_t>(1, std::min<int64_t>(RED_BLOCK / tcol_limit, pow2_floor(std::max<int64_t>(1, n_red / unroll))));
         d.tcol = (int)std::min<int64_t>(RED_BLOCK / rw_want, pow2_ceil(d.packs0));
         d.n_out = n_out / d.kshape[0];
         d.n_items = n_red;
